@@ -1,0 +1,97 @@
+"""ctypes binding of libgrl_b200.so (include/grl_b200.h).  This is the only place the Python surface
+touches native code; there is no CPU or eager-PyTorch fallback: a missing library or a non-CUDA tensor is an
+error."""
+import ctypes
+import os
+import re
+
+import torch
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libgrl_b200.so")
+HEADER_PATH = os.path.join(os.path.dirname(_PKG), "include", "grl_b200.h")
+
+c_int, c_i64, c_f32, c_vp, c_sz = ctypes.c_int, ctypes.c_int64, ctypes.c_float, ctypes.c_void_p, ctypes.c_size_t
+
+
+class GrlGrid(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int32) for n in ("H", "W", "wh", "ww", "sh", "sw")]
+
+    def __repr__(self):
+        return f"GrlGrid({self.H}x{self.W}, win {self.wh}x{self.ww}, shift {self.sh},{self.sw})"
+
+
+def grid(H, W, wh, ww, sh=0, sw=0):
+    return GrlGrid(int(H), int(W), int(wh), int(ww), int(sh), int(sw))
+
+
+_SIGNATURES = {
+    "grl_last_error": (ctypes.c_char_p, []),
+    "grl_abi_version": (c_int, []),
+    "grl_device_ok": (c_int, []),
+    "grl_rel_index_host": (c_int, [c_int, c_int, c_int, c_int, c_vp]),
+    "grl_shift_mask_host": (c_int, [c_int] * 8 + [c_vp]),
+    "grl_coords_table_host": (c_int, [c_int, c_int, c_int, c_vp]),
+    "grl_bias_table_f32": (c_int, [c_vp, c_int, c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_vp]),
+    "grl_affine_f32": (c_int, [c_vp, c_i64, c_int, c_int, c_int, c_vp, c_vp, c_int, c_vp, c_vp, c_int, c_vp]),
+    "grl_linear_f32": (c_int, [c_vp, c_i64, c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_i64, c_int, c_int, c_int, c_f32, c_vp]),
+    "grl_conv3x3_f32": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_f32, c_vp]),
+    "grl_avgpool_f32": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp]),
+    "grl_ln_residual_f32": (c_int, [c_vp, c_vp, c_vp, c_vp, c_f32, c_f32, c_vp, c_vp, c_i64, c_vp, c_i64, c_int, c_vp]),
+    "grl_channel_gate_workspace": (c_sz, [c_int, c_i64, c_int]),
+    "grl_channel_gate_f32": (c_int, [c_vp, c_int, c_i64, c_int, c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_vp, c_sz, c_vp]),
+    "grl_window_attn_f32": (c_int, [c_vp, c_i64, c_vp, c_i64, c_int, GrlGrid, c_int, c_int, c_vp, c_vp, c_int, c_vp]),
+    "grl_stripe_attn_workspace": (c_sz, [c_int, GrlGrid, GrlGrid, c_int, c_int]),
+    "grl_stripe_attn_f32": (c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_int, GrlGrid, GrlGrid, c_int, c_int,
+                                    c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_sz, c_vp]),
+}
+
+_lib = None
+
+
+def header_symbols():
+    """Every function name declared in include/grl_b200.h."""
+    with open(HEADER_PATH) as f:
+        src = re.sub(r"/\*.*?\*/", "", f.read(), flags=re.S)
+    return sorted(set(re.findall(r"\b(grl_[a-z0-9_]+)\s*\(", src)))
+
+
+def lib():
+    """Loads the library (never builds it implicitly on a GPU box: the .so ships with the snapshot)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(there is no CPU / eager fallback for the GRL hot path)")
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype, fn.argtypes = res, args
+        if handle.grl_abi_version() != 1:
+            raise RuntimeError("libgrl_b200.so ABI version mismatch")
+        _lib = handle
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise RuntimeError(f"grl_b200 error {rc}: {lib().grl_last_error().decode()}")
+
+
+def ptr(t):
+    """Device pointer of a contiguous CUDA tensor (None -> NULL)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("grl_b200 operators need CUDA tensors (no CPU fallback)")
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def require_device(t):
+    if not t.is_cuda:
+        raise RuntimeError("grl_b200: input is not on a CUDA device; the B200 kernels have no CPU fallback")

@@ -1,0 +1,194 @@
+// capi.cu -- the extern "C" surface declared in include/grl_b200.h.
+#include <math.h>
+#include <string.h>
+
+#include "grl_common.cuh"
+#include "ops_f32.h"
+
+namespace grl {
+char* error_buffer() {
+  static thread_local char buf[512] = {0};
+  return buf;
+}
+}  // namespace grl
+
+using namespace grl;
+
+extern "C" {
+
+const char* grl_last_error(void) { return error_buffer(); }
+int grl_abi_version(void) { return GRL_B200_ABI_VERSION; }
+
+int grl_device_ok(void) {
+  int dev = 0, major = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return 0;
+  return major == 10;
+}
+
+// ---------------------------------------------------------------- geometry (host)
+int grl_rel_index_host(int wh, int ww, int df, int window_to_anchor, int64_t* out) {
+  GRL_REQUIRE(wh > 0 && ww > 0 && df > 0 && out, "rel_index: bad arguments");
+  const int awh = wh / df, aww = ww / df;
+  const int n1 = window_to_anchor ? wh * ww : awh * aww;
+  const int n2 = window_to_anchor ? awh * aww : wh * ww;
+  const int qww = window_to_anchor ? ww : aww;
+  const int kwh = window_to_anchor ? awh : wh, kww = window_to_anchor ? aww : ww;
+  for (int i = 0; i < n1; ++i)
+    for (int j = 0; j < n2; ++j)
+      out[(size_t)i * n2 + j] = rel_index(i / qww, i % qww, j / kww, j % kww, qww, kwh, kww);
+  return GRL_OK;
+}
+
+int grl_shift_mask_host(int H, int W, int wh, int ww, int sh, int sw, int df, int window_to_anchor, float* out) {
+  GRL_REQUIRE(df > 0 && out, "shift_mask: bad arguments");
+  GrlGrid gt = {H, W, wh, ww, sh, sw};
+  GrlGrid ga = {H / df, W / df, wh / df, ww / df, sh / df, sw / df};
+  int rc;
+  if ((rc = check_grid(gt, "shift_mask(tokens)")) != GRL_OK) return rc;
+  if ((rc = check_grid(ga, "shift_mask(anchors)")) != GRL_OK) return rc;
+  const GrlGrid& gq = window_to_anchor ? gt : ga;
+  const GrlGrid& gk = window_to_anchor ? ga : gt;
+  const int n1 = gq.wh * gq.ww, n2 = gk.wh * gk.ww;
+  const int nwh = gq.H / gq.wh, nww = gq.W / gq.ww;
+  for (int wr = 0; wr < nwh; ++wr)
+    for (int wc = 0; wc < nww; ++wc) {
+      float* o = out + (size_t)(wr * nww + wc) * n1 * n2;
+      for (int i = 0; i < n1; ++i) {
+        Tok tq = locate(gq, wr, wc, i);
+        const int rq = region_id(gq, tq.r, tq.c);
+        for (int j = 0; j < n2; ++j) {
+          Tok tk = locate(gk, wr, wc, j);
+          o[(size_t)i * n2 + j] = (rq != region_id(gk, tk.r, tk.c)) ? -100.0f : 0.0f;
+        }
+      }
+    }
+  return GRL_OK;
+}
+
+int grl_coords_table_host(int wh, int ww, int df, float* out) {
+  GRL_REQUIRE(wh > 0 && ww > 0 && df > 0 && out, "coords_table: bad arguments");
+  const int ws[2] = {wh, ww}, aws[2] = {wh / df, ww / df};
+  int hi[2], lo[2];
+  for (int a = 0; a < 2; ++a) {
+    hi[a] = ws[a] - 1 - (ws[a] - aws[a]) / 2;
+    lo[a] = -(aws[a] - 1) - (ws[a] - aws[a]) / 2;
+  }
+  const int nh = hi[0] - lo[0] + 1, nw = hi[1] - lo[1] + 1;
+  // same operation order as ops.py:257-269: v / hi (fp32), * 8 (fp32), sign * log2(|v| + 1) (fp32), then a
+  // division by the float64 scalar np.log2(8) == 3.0 carried out in fp32 (torch keeps the tensor dtype).
+  for (int i = 0; i < nh; ++i)
+    for (int j = 0; j < nw; ++j) {
+      const int c[2] = {lo[0] + i, lo[1] + j};
+      for (int a = 0; a < 2; ++a) {
+        float v = (float)c[a] / (float)hi[a];
+        v = v * 8.0f;
+        float s = (v > 0.f) ? 1.f : (v < 0.f ? -1.f : 0.f);
+        out[((size_t)i * nw + j) * 2 + a] = s * log2f(fabsf(v) + 1.0f) / 3.0f;
+      }
+    }
+  return GRL_OK;
+}
+
+// ---------------------------------------------------------------- fp32 operators
+int grl_bias_table_f32(const float* table, int rows, const float* w1, const float* b1, const float* w2, int hidden,
+                       int heads, float* out, void* stream) {
+  return launch_bias_table(table, rows, w1, b1, w2, hidden, heads, out, (cudaStream_t)stream);
+}
+
+int grl_affine_f32(float* attn, int64_t B_, int heads, int n1, int n2, const float* logit_scale, const float* bias,
+                   int rows, const int64_t* index, const float* mask, int nW, void* stream) {
+  return launch_affine(attn, B_, heads, n1, n2, logit_scale, bias, rows, (const long long*)index, mask, nW,
+                       (cudaStream_t)stream);
+}
+
+int grl_linear_f32(const float* x, int64_t ldx, const float* w, const float* b, const float* res, int64_t ldr,
+                   float* y, int64_t ldy, int64_t M, int N, int K, int act, float slope, void* stream) {
+  GRL_REQUIRE(M >= 0 && N >= 0 && K > 0 && ldx >= K && ldy >= N, "linear: bad shape M=%lld N=%d K=%d", (long long)M, N,
+              K);
+  GemmArgs a = {x, ldx, w, b, res, ldr, y, ldy, M, N, K, act, slope, 0, 0, 0};
+  return launch_gemm(a, false, (cudaStream_t)stream);
+}
+
+int grl_conv3x3_f32(const float* x, const float* w, const float* b, const float* res, float* y, int B, int H, int W,
+                    int Cin, int Cout, int act, float slope, void* stream) {
+  GRL_REQUIRE(B >= 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, "conv3x3: bad shape");
+  GemmArgs a = {x, 0, w, b, res, Cout, y, Cout, (long long)B * H * W, Cout, 9 * Cin, act, slope, H, W, Cin};
+  return launch_gemm(a, true, (cudaStream_t)stream);
+}
+
+int grl_avgpool_f32(const float* x, float* y, int B, int H, int W, int C, int df, void* stream) {
+  return launch_avgpool(x, y, B, H, W, C, df, (cudaStream_t)stream);
+}
+
+int grl_ln_residual_f32(const float* x, const float* u, const float* gamma, const float* beta, float eps,
+                        float res_scale, const float* cab_y, const float* cab_gate, int64_t L, float* out, int64_t M,
+                        int C, void* stream) {
+  return launch_ln_residual(x, u, gamma, beta, eps, res_scale, cab_y, cab_gate, L, out, M, C, (cudaStream_t)stream);
+}
+
+size_t grl_channel_gate_workspace(int B, int64_t L, int C) { return channel_gate_ws(B, L, C); }
+
+int grl_channel_gate_f32(const float* y, int B, int64_t L, int C, const float* w1, const float* b1, const float* w2,
+                         const float* b2, int R, float* gate, void* workspace, size_t workspace_bytes, void* stream) {
+  return launch_channel_gate(y, B, L, C, w1, b1, w2, b2, R, gate, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int grl_window_attn_f32(const float* qkv, int64_t ld_qkv, float* out, int64_t ld_out, int B, GrlGrid grid, int heads,
+                        int d, const float* logit_scale, const float* bias, int use_mask, void* stream) {
+  AttnArgs a;
+  memset(&a, 0, sizeof(a));
+  const int c = heads * d;
+  a.gq = grid;
+  a.gk = grid;
+  a.q = qkv, a.ldq = ld_qkv, a.q_off = 0;
+  a.k = qkv, a.ldk = ld_qkv, a.k_off = c;
+  a.v = qkv, a.ldv = ld_qkv, a.v_off = 2 * c;
+  a.out = out, a.ldo = ld_out, a.o_off = 0;
+  a.B = B, a.heads = heads, a.d = d;
+  a.logit_scale = logit_scale;
+  a.bias = bias;
+  a.rows = (2 * grid.wh - 1) * (2 * grid.ww - 1);
+  a.use_mask = use_mask;
+  return launch_attn(a, (cudaStream_t)stream);
+}
+
+size_t grl_stripe_attn_workspace(int B, GrlGrid tok, GrlGrid anc, int heads, int d) {
+  (void)tok;
+  return sizeof(float) * (size_t)B * anc.H * anc.W * heads * d;
+}
+
+int grl_stripe_attn_f32(const float* qkv, int64_t ld_qkv, const float* anchor, int64_t ld_anchor, float* out,
+                        int64_t ld_out, int B, GrlGrid tok, GrlGrid anc, int heads, int d, const float* logit_scale1,
+                        const float* bias1, const float* logit_scale2, const float* bias2, int use_mask,
+                        void* workspace, size_t workspace_bytes, void* stream) {
+  const size_t need = grl_stripe_attn_workspace(B, tok, anc, heads, d);
+  if (workspace_bytes < need) return fail(GRL_ERR_WORKSPACE, "stripe_attn: workspace %zu < %zu", workspace_bytes, need);
+  const int c = heads * d;
+  const int rows = (tok.wh + anc.wh - 1) * (tok.ww + anc.ww - 1);
+  float* x1 = (float*)workspace;
+  AttnArgs a;
+  memset(&a, 0, sizeof(a));
+  // pass 1: anchors attend to the stripe's tokens (a2w)   efficient.py:256-258
+  a.gq = anc, a.gk = tok;
+  a.q = anchor, a.ldq = ld_anchor, a.q_off = 0;
+  a.k = qkv, a.ldk = ld_qkv, a.k_off = c;
+  a.v = qkv, a.ldv = ld_qkv, a.v_off = 2 * c;
+  a.out = x1, a.o_dense = 1;
+  a.B = B, a.heads = heads, a.d = d;
+  a.logit_scale = logit_scale1, a.bias = bias1, a.rows = rows, a.use_mask = use_mask;
+  int rc = launch_attn(a, (cudaStream_t)stream);
+  if (rc != GRL_OK) return rc;
+  // pass 2: tokens attend to the anchors, values = X1 (w2a)   efficient.py:259
+  memset(&a, 0, sizeof(a));
+  a.gq = tok, a.gk = anc;
+  a.q = qkv, a.ldq = ld_qkv, a.q_off = 0;
+  a.k = anchor, a.ldk = ld_anchor, a.k_off = 0;
+  a.v = x1, a.v_dense = 1;
+  a.out = out, a.ldo = ld_out, a.o_off = 0;
+  a.B = B, a.heads = heads, a.d = d;
+  a.logit_scale = logit_scale2, a.bias = bias2, a.rows = rows, a.use_mask = use_mask;
+  return launch_attn(a, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,732 @@
+"""The reference's nn.Module surface for the GRL forward path, re-implemented on the sm_100a kernels.
+
+Class names, constructor signatures, parameter names/shapes and forward signatures
+follow the reference so that `hydra.utils.instantiate(_target_=...GRL)`, `load_state_dict(strict=True)`,
+`convert_checkpoint` and `self.model(x)` in the LightningIR engine keep working (engines/base.py:44,:106,:177;
+tools/trainer.py:93-115).  Differences, all deliberate:
+  * inference only (the engine's validation path runs under torch.no_grad()); no autograd support;
+  * every forward runs hand-written CUDA through libgrl_b200.so - CPU tensors raise, there is no fallback;
+  * relative-position indices and shift masks are closed forms inside the kernels, so the `index*` / `mask*`
+    arguments are accepted but only their None-ness is used (mask None = unshifted block).
+Reference files: models/networks/grl.py, models/common/mixed_attn_block_efficient.py,
+models/common/mixed_attn_block.py, models/common/swin_v1_block.py, models/common/upsample.py.
+"""
+import math
+from types import SimpleNamespace
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import functional as K
+from . import geometry as G
+from .geometry import to_2tuple, _get_stripe_info
+
+_LN_MAX = math.log(1.0 / 0.01)
+
+
+def _closed_form_marker(device=None):
+    """Placeholder standing for an index / mask tensor that the kernels evaluate in closed form."""
+    return torch.empty(0, device=device)
+
+
+class _PackedConv:
+    """Caches the (Cout, 9*Cin) im2col-ordered copy of an nn.Conv2d weight (re-packed when the weight changes)."""
+
+    def __init__(self):
+        self._key, self._w = None, None
+
+    def get(self, conv):
+        w = conv.weight
+        key = (w.data_ptr(), w._version, w.device)
+        if key != self._key:
+            self._w, self._key = K.pack_conv_weight(w), key
+        return self._w
+
+
+def conv2d_cl(conv, cache, x, act=K.ACT_NONE, slope=0.0, res=None):
+    """nn.Conv2d(3x3, stride 1, pad 1) applied to channels-last x (B, H, W, Cin)."""
+    return K.conv3x3(x, cache.get(conv), conv.bias, act, slope, res)
+
+
+def pixel_shuffle_cl(x, r):
+    """nn.PixelShuffle(r) on channels-last data: (B, H, W, C*r*r) -> (B, H*r, W*r, C)."""
+    B, H, W, Crr = x.shape
+    C = Crr // (r * r)
+    return x.view(B, H, W, C, r, r).permute(0, 1, 4, 2, 5, 3).reshape(B, H * r, W * r, C)
+
+
+# ----------------------------------------------------------------------------------------------
+# attention
+# ----------------------------------------------------------------------------------------------
+class CPB_MLP(nn.Sequential):
+    """mixed_attn_block.py:24-31."""
+
+    def __init__(self, in_channels, out_channels, channels=512):
+        super().__init__(nn.Linear(in_channels, channels, bias=True), nn.ReLU(inplace=True),
+                         nn.Linear(channels, out_channels, bias=False))
+
+
+class AffineTransform(nn.Module):
+    """mixed_attn_block_efficient.py:23-58: learned per-head logit scale + continuous position bias (+ mask)."""
+
+    def __init__(self, num_heads):
+        super().__init__()
+        self.logit_scale = nn.Parameter(torch.log(10 * torch.ones((num_heads, 1, 1))), requires_grad=True)
+        self.cpb_mlp = CPB_MLP(2, num_heads)
+
+    def bias_table(self, relative_coords_table):
+        """(heads, rows) = 16*sigmoid(cpb_mlp(table)) -- what the fused attention kernels consume."""
+        return K.bias_table(relative_coords_table, self.cpb_mlp[0].weight, self.cpb_mlp[0].bias, self.cpb_mlp[2].weight)
+
+    @torch.no_grad()
+    def forward(self, attn, relative_coords_table, relative_position_index, mask):
+        bias = self.bias_table(relative_coords_table)
+        return K.affine_(attn.clone(), self.logit_scale, bias, relative_position_index, mask)
+
+
+class WindowAttention(nn.Module):
+    """mixed_attn_block_efficient.py:97-171.  qkv is the input of forward."""
+
+    def __init__(self, input_resolution, window_size, num_heads, window_shift=False, attn_drop=0.0,
+                 pretrained_window_size=[0, 0], args=None):
+        super().__init__()
+        self.input_resolution = input_resolution
+        self.window_size = to_2tuple(window_size)
+        self.pretrained_window_size = pretrained_window_size
+        self.num_heads = num_heads
+        self.shift_size = self.window_size[0] // 2 if window_shift else 0
+        self.euclidean_dist = bool(getattr(args, "euclidean_dist", False))
+        if self.euclidean_dist:
+            raise NotImplementedError("euclidean_dist is an ablation outside the B200 hot path")
+        self.attn_transform = AffineTransform(num_heads)
+        self.attn_drop = nn.Dropout(attn_drop)
+        self.softmax = nn.Softmax(dim=-1)
+
+    @torch.no_grad()
+    def forward(self, qkv, x_size, table, index, mask, out=None):
+        """qkv (B, L, 3c) -> (B, L, c).  `index` is unused (closed form); `mask is not None` enables the shift mask."""
+        B, L, C = qkv.shape
+        s = self.shift_size
+        grid = G.token_grid(x_size, self.window_size, (s, s))
+        bias = self.attn_transform.bias_table(table)
+        return K.window_attention(qkv, B, grid, self.num_heads, self.attn_transform.logit_scale, bias,
+                                  mask is not None, out)
+
+    def extra_repr(self):
+        return (f"window_size={self.window_size}, shift_size={self.shift_size}, "
+                f"pretrained_window_size={self.pretrained_window_size}, num_heads={self.num_heads}")
+
+
+class AnchorStripeAttention(nn.Module):
+    """mixed_attn_block_efficient.py:177-276."""
+
+    def __init__(self, input_resolution, stripe_size, stripe_groups, stripe_shift, num_heads, attn_drop=0.0,
+                 pretrained_stripe_size=[0, 0], anchor_window_down_factor=1, args=None):
+        super().__init__()
+        self.input_resolution = input_resolution
+        self.stripe_size = stripe_size
+        self.stripe_groups = stripe_groups
+        self.stripe_shift = stripe_shift
+        self.num_heads = num_heads
+        self.pretrained_stripe_size = pretrained_stripe_size
+        self.anchor_window_down_factor = anchor_window_down_factor
+        self.euclidean_dist = bool(getattr(args, "euclidean_dist", False))
+        if self.euclidean_dist:
+            raise NotImplementedError("euclidean_dist is an ablation outside the B200 hot path")
+        self.attn_transform1 = AffineTransform(num_heads)
+        self.attn_transform2 = AffineTransform(num_heads)
+        self.attn_drop = nn.Dropout(attn_drop)
+        self.softmax = nn.Softmax(dim=-1)
+
+    def grids(self, x_size):
+        ss, sh = _get_stripe_info(self.stripe_size, self.stripe_groups, self.stripe_shift, x_size)
+        df = self.anchor_window_down_factor
+        return G.token_grid(x_size, ss, sh), G.anchor_grid(x_size, ss, sh, df)
+
+    @torch.no_grad()
+    def forward(self, qkv, anchor, x_size, table, index_a2w, index_w2a, mask_a2w, mask_w2a, out=None):
+        B, L, C = qkv.shape
+        tok, anc = self.grids(x_size)
+        b1 = self.attn_transform1.bias_table(table)
+        b2 = self.attn_transform2.bias_table(table)
+        return K.stripe_attention(qkv, anchor, B, tok, anc, self.num_heads, self.attn_transform1.logit_scale, b1,
+                                  self.attn_transform2.logit_scale, b2, mask_a2w is not None, out)
+
+    def extra_repr(self):
+        return (f"stripe_size={self.stripe_size}, stripe_groups={self.stripe_groups}, stripe_shift={self.stripe_shift}, "
+                f"pretrained_stripe_size={self.pretrained_stripe_size}, num_heads={self.num_heads}, "
+                f"anchor_window_down_factor={self.anchor_window_down_factor}")
+
+
+class QKVProjection(nn.Module):
+    """mixed_attn_block.py:661-676 (proj_type 'linear' -- the only one any released config uses)."""
+
+    def __init__(self, dim, qkv_bias, proj_type, args):
+        super().__init__()
+        if proj_type != "linear":
+            raise NotImplementedError(f"qkv_proj_type={proj_type!r}: only 'linear' is on the B200 hot path")
+        self.proj_type = proj_type
+        self.body = nn.Linear(dim, dim * 3, bias=qkv_bias)
+
+    @torch.no_grad()
+    def forward(self, x, x_size):
+        return K.linear(x, self.body.weight, self.body.bias)
+
+
+class AnchorLinear(nn.Module):
+    """mixed_attn_block.py:714-736: AvgPool2d(df) then Linear(C -> C/2); returns (B, H/df, W/df, C/2)."""
+
+    def __init__(self, in_channels, out_channels, down_factor, pooling_mode, bias):
+        super().__init__()
+        if pooling_mode != "avgpool":
+            raise NotImplementedError(f"anchor pooling {pooling_mode!r}: only 'avgpool' is on the B200 hot path")
+        self.down_factor = down_factor
+        self.pooling = nn.AvgPool2d(down_factor, down_factor)
+        self.reduction = nn.Linear(in_channels, out_channels, bias=bias)
+
+    @torch.no_grad()
+    def forward(self, x, x_size):
+        B, L, C = x.shape
+        pooled = K.avgpool(x.view(B, x_size[0], x_size[1], C), self.down_factor)
+        return K.linear(pooled, self.reduction.weight, self.reduction.bias)
+
+
+class AnchorProjection(nn.Module):
+    """mixed_attn_block.py:739-785 (one-stage avgpool variant)."""
+
+    def __init__(self, dim, proj_type, one_stage, anchor_window_down_factor, args):
+        super().__init__()
+        if not one_stage or proj_type.find("pool") < 0:
+            raise NotImplementedError("only the one-stage avgpool anchor projection is on the B200 hot path")
+        self.proj_type = proj_type
+        self.body = nn.ModuleList([AnchorLinear(dim, dim // 2, anchor_window_down_factor, proj_type, True)])
+
+    def forward(self, x, x_size):
+        for m in self.body:
+            x = m(x, x_size)
+        return x
+
+
+class MixedAttention(nn.Module):
+    """mixed_attn_block_efficient.py:282-403: shared QKV / anchor projections, window + stripe attention, proj."""
+
+    def __init__(self, dim, input_resolution, num_heads_w, num_heads_s, window_size, window_shift, stripe_size,
+                 stripe_groups, stripe_shift, qkv_bias=True, qkv_proj_type="linear", anchor_proj_type="separable_conv",
+                 anchor_one_stage=True, anchor_window_down_factor=1, attn_drop=0.0, proj_drop=0.0,
+                 pretrained_window_size=[0, 0], pretrained_stripe_size=[0, 0], args=None):
+        super().__init__()
+        self.dim = dim
+        self.input_resolution = input_resolution
+        self.args = args
+        self.qkv = QKVProjection(dim, qkv_bias, qkv_proj_type, args)
+        self.anchor = AnchorProjection(dim, anchor_proj_type, anchor_one_stage, anchor_window_down_factor, args)
+        self.window_attn = WindowAttention(input_resolution, window_size, num_heads_w, window_shift, attn_drop,
+                                           pretrained_window_size, args)
+        self.stripe_attn = AnchorStripeAttention(input_resolution, stripe_size, stripe_groups, stripe_shift,
+                                                 num_heads_s, attn_drop, pretrained_stripe_size,
+                                                 anchor_window_down_factor, args)
+        self.proj = nn.Linear(dim, dim)
+        self.proj_drop = nn.Dropout(proj_drop)
+
+    @torch.no_grad()
+    def forward(self, x, x_size, table_index_mask):
+        B, L, C = x.shape
+        qkv = self.qkv(x, x_size)
+        qkv_window, qkv_stripe = torch.split(qkv, C * 3 // 2, dim=-1)
+        anchor = self.anchor(x, x_size)
+        merged = torch.empty(B, L, C, device=x.device, dtype=torch.float32)  # cat([window, stripe]) without the copy
+        t = table_index_mask
+        self.window_attn(qkv_window, x_size, t["table_w"], t["index_w"], t["mask_w"], out=merged[..., : C // 2])
+        self.stripe_attn(qkv_stripe, anchor, x_size, t["table_s"], t["index_a2w"], t["index_w2a"], t["mask_a2w"],
+                         t["mask_w2a"], out=merged[..., C // 2:])
+        return K.linear(merged, self.proj.weight, self.proj.bias)
+
+    def extra_repr(self):
+        return f"dim={self.dim}, input_resolution={self.input_resolution}"
+
+
+# ----------------------------------------------------------------------------------------------
+# conv / channel-attention block, MLP
+# ----------------------------------------------------------------------------------------------
+class ChannelAttention(nn.Module):
+    """mixed_attn_block.py:948-967."""
+
+    def __init__(self, num_feat, reduction=16):
+        super().__init__()
+        self.attention = nn.Sequential(nn.AdaptiveAvgPool2d(1), nn.Conv2d(num_feat, num_feat // reduction, 1, padding=0),
+                                       nn.ReLU(inplace=True), nn.Conv2d(num_feat // reduction, num_feat, 1, padding=0),
+                                       nn.Sigmoid())
+
+    @torch.no_grad()
+    def gate(self, y):
+        """y (B, L, C) channels-last -> (B, C) sigmoid gate."""
+        a1, a3 = self.attention[1], self.attention[3]
+        return K.channel_gate(y, a1.weight.view(a1.weight.shape[0], -1), a1.bias,
+                              a3.weight.view(a3.weight.shape[0], -1), a3.bias)
+
+    @torch.no_grad()
+    def forward(self, x):
+        """x (B, C, H, W) like the reference."""
+        B, C, H, W = x.shape
+        y = x.permute(0, 2, 3, 1).reshape(B, H * W, C).contiguous()
+        return x * self.gate(y).view(B, C, 1, 1)
+
+
+class CAB(nn.Module):
+    """mixed_attn_block.py:970-983: conv3x3(C->C/4) GELU conv3x3(C/4->C) ChannelAttention, on (B, L, C)."""
+
+    def __init__(self, num_feat, compress_ratio=4, reduction=18):
+        super().__init__()
+        self.cab = nn.Sequential(nn.Conv2d(num_feat, num_feat // compress_ratio, 3, 1, 1), nn.GELU(),
+                                 nn.Conv2d(num_feat // compress_ratio, num_feat, 3, 1, 1),
+                                 ChannelAttention(num_feat, reduction))
+        self._p0, self._p2 = _PackedConv(), _PackedConv()
+
+    @torch.no_grad()
+    def features_and_gate(self, x, x_size):
+        """Returns (y, gate): y (B, L, C) = conv2(gelu(conv1(x))), gate (B, C); CAB(x) = y * gate."""
+        B, L, C = x.shape
+        t = conv2d_cl(self.cab[0], self._p0, x.view(B, x_size[0], x_size[1], C), K.ACT_GELU)
+        y = conv2d_cl(self.cab[2], self._p2, t).view(B, L, C)
+        return y, self.cab[3].gate(y)
+
+    @torch.no_grad()
+    def forward(self, x, x_size):
+        y, g = self.features_and_gate(x, x_size)
+        return y * g.unsqueeze(1)
+
+
+class Mlp(nn.Module):
+    """swin_v1_block.py:15-43 (GELU is the exact erf form)."""
+
+    def __init__(self, in_features, hidden_features=None, out_features=None, act_layer=nn.GELU, drop=0.0):
+        super().__init__()
+        out_features = out_features or in_features
+        hidden_features = hidden_features or in_features
+        if act_layer is not nn.GELU:
+            raise NotImplementedError("only nn.GELU is on the B200 hot path")
+        drop_probs = to_2tuple(drop)
+        self.fc1 = nn.Linear(in_features, hidden_features)
+        self.act = act_layer()
+        self.drop1 = nn.Dropout(drop_probs[0])
+        self.fc2 = nn.Linear(hidden_features, out_features)
+        self.drop2 = nn.Dropout(drop_probs[1])
+
+    @torch.no_grad()
+    def forward(self, x):
+        return K.linear(K.linear(x, self.fc1.weight, self.fc1.bias, K.ACT_GELU), self.fc2.weight, self.fc2.bias)
+
+
+class EfficientMixAttnTransformerBlock(nn.Module):
+    """mixed_attn_block_efficient.py:406-564: post-norm residual block
+    x = x + rs*LN1(attn(x)) [+ CAB(x)];  x = x + rs*LN2(mlp(x))."""
+
+    def __init__(self, dim, input_resolution, num_heads_w, num_heads_s, window_size=7, window_shift=False,
+                 stripe_size=[8, 8], stripe_groups=[None, None], stripe_shift=False, stripe_type="H", mlp_ratio=4.0,
+                 qkv_bias=True, qkv_proj_type="linear", anchor_proj_type="separable_conv", anchor_one_stage=True,
+                 anchor_window_down_factor=1, drop=0.0, attn_drop=0.0, drop_path=0.0, act_layer=nn.GELU,
+                 norm_layer=nn.LayerNorm, pretrained_window_size=[0, 0], pretrained_stripe_size=[0, 0], res_scale=1.0,
+                 args=None):
+        super().__init__()
+        self.dim = dim
+        self.input_resolution = input_resolution
+        self.num_heads_w = num_heads_w
+        self.num_heads_s = num_heads_s
+        self.window_size = window_size
+        self.window_shift = window_shift
+        self.stripe_shift = stripe_shift
+        self.stripe_type = stripe_type
+        self.args = args
+        if self.stripe_type == "W":
+            self.stripe_size = stripe_size[::-1]
+            self.stripe_groups = stripe_groups[::-1]
+        else:
+            self.stripe_size = stripe_size
+            self.stripe_groups = stripe_groups
+        self.mlp_ratio = mlp_ratio
+        self.res_scale = res_scale
+        if norm_layer is not nn.LayerNorm:
+            raise NotImplementedError("only nn.LayerNorm is on the B200 hot path")
+        self.attn = MixedAttention(dim, input_resolution, num_heads_w, num_heads_s, window_size, window_shift,
+                                   self.stripe_size, self.stripe_groups, stripe_shift, qkv_bias, qkv_proj_type,
+                                   anchor_proj_type, anchor_one_stage, anchor_window_down_factor, attn_drop, drop,
+                                   pretrained_window_size, pretrained_stripe_size, args)
+        self.norm1 = norm_layer(dim)
+        if self.args.local_connection:
+            self.conv = CAB(dim)
+        self.drop_path = nn.Identity()  # stochastic depth is the identity at inference (timm DropPath in eval)
+        self.mlp = Mlp(in_features=dim, hidden_features=int(dim * mlp_ratio), act_layer=act_layer, drop=drop)
+        self.norm2 = norm_layer(dim)
+
+    def _get_table_index_mask(self, all_table_index_mask):
+        """mixed_attn_block_efficient.py:510-537."""
+        a = all_table_index_mask
+        d = "sv" if self.stripe_type == "W" else "sh"
+        return {
+            "table_w": a["table_w"], "index_w": a["index_w"],
+            "table_s": a["table_" + d], "index_a2w": a[f"index_{d}_a2w"], "index_w2a": a[f"index_{d}_w2a"],
+            "mask_w": a["mask_w"] if self.window_shift else None,
+            "mask_a2w": a[f"mask_{d}_a2w"] if self.stripe_shift else None,
+            "mask_w2a": a[f"mask_{d}_w2a"] if self.stripe_shift else None,
+        }
+
+    @torch.no_grad()
+    def forward(self, x, x_size, all_table_index_mask):
+        t = self._get_table_index_mask(all_table_index_mask)
+        u = self.attn(x, x_size, t)
+        if self.args.local_connection:
+            y, gate = self.conv.features_and_gate(x, x_size)
+            x = K.ln_residual(x, u, self.norm1.weight, self.norm1.bias, self.norm1.eps, self.res_scale, y, gate)
+        else:
+            x = K.ln_residual(x, u, self.norm1.weight, self.norm1.bias, self.norm1.eps, self.res_scale)
+        return K.ln_residual(x, self.mlp(x), self.norm2.weight, self.norm2.bias, self.norm2.eps, self.res_scale)
+
+    def extra_repr(self):
+        return (f"dim={self.dim}, input_resolution={self.input_resolution}, num_heads=({self.num_heads_w}, "
+                f"{self.num_heads_s}), window_size={self.window_size}, window_shift={self.window_shift}, "
+                f"stripe_size={self.stripe_size}, stripe_groups={self.stripe_groups}, stripe_shift={self.stripe_shift}, "
+                f"self.stripe_type={self.stripe_type}, mlp_ratio={self.mlp_ratio}, res_scale={self.res_scale}")
+
+
+def build_last_conv(conv_type, dim):
+    """swin_v1_block.py:469-485 ('1conv' is what every GRL config uses)."""
+    if conv_type != "1conv":
+        raise NotImplementedError(f"conv_type={conv_type!r}: only '1conv' is on the B200 hot path")
+    return nn.Conv2d(dim, dim, 3, 1, 1)
+
+
+class Upsample(nn.Module):
+    """upsample.py:6-30."""
+
+    def __init__(self, scale, num_feat):
+        super().__init__()
+        m = []
+        if (scale & (scale - 1)) == 0:
+            for _ in range(int(math.log(scale, 2))):
+                m += [nn.Conv2d(num_feat, 4 * num_feat, 3, 1, 1), nn.PixelShuffle(2)]
+        elif scale == 3:
+            m += [nn.Conv2d(num_feat, 9 * num_feat, 3, 1, 1), nn.PixelShuffle(3)]
+        else:
+            raise ValueError(f"scale {scale} is not supported. Supported scales: 2^n and 3.")
+        self.up = nn.Sequential(*m)
+        self._packs = [_PackedConv() for _ in m]
+
+    @torch.no_grad()
+    def forward_cl(self, x):
+        for i, m in enumerate(self.up):
+            x = conv2d_cl(m, self._packs[i], x) if isinstance(m, nn.Conv2d) else pixel_shuffle_cl(x, m.upscale_factor)
+        return x
+
+    def forward(self, x):
+        return self.forward_cl(x.permute(0, 2, 3, 1).contiguous()).permute(0, 3, 1, 2)
+
+
+class UpsampleOneStep(nn.Module):
+    """upsample.py:33-50."""
+
+    def __init__(self, scale, num_feat, num_out_ch):
+        super().__init__()
+        self.num_feat = num_feat
+        self.up = nn.Sequential(nn.Conv2d(num_feat, (scale ** 2) * num_out_ch, 3, 1, 1), nn.PixelShuffle(scale))
+        self._pack = _PackedConv()
+
+    @torch.no_grad()
+    def forward_cl(self, x):
+        return pixel_shuffle_cl(conv2d_cl(self.up[0], self._pack, x), self.up[1].upscale_factor)
+
+    def forward(self, x):
+        return self.forward_cl(x.permute(0, 2, 3, 1).contiguous()).permute(0, 3, 1, 2)
+
+
+# ----------------------------------------------------------------------------------------------
+# stage / network
+# ----------------------------------------------------------------------------------------------
+class TransformerStage(nn.Module):
+    """models/networks/grl.py:31-173: `depth` blocks, then conv3x3 + residual."""
+
+    def __init__(self, dim, input_resolution, depth, num_heads_window, num_heads_stripe, window_size, stripe_size,
+                 stripe_groups, stripe_shift, mlp_ratio=4.0, qkv_bias=True, qkv_proj_type="linear",
+                 anchor_proj_type="avgpool", anchor_one_stage=True, anchor_window_down_factor=1, drop=0.0,
+                 attn_drop=0.0, drop_path=0.0, norm_layer=nn.LayerNorm, pretrained_window_size=[0, 0],
+                 pretrained_stripe_size=[0, 0], conv_type="1conv", init_method="", fairscale_checkpoint=False,
+                 offload_to_cpu=False, args=None):
+        super().__init__()
+        self.dim = dim
+        self.input_resolution = input_resolution
+        self.init_method = init_method
+        self.blocks = nn.ModuleList()
+        for i in range(depth):
+            self.blocks.append(EfficientMixAttnTransformerBlock(
+                dim=dim, input_resolution=input_resolution, num_heads_w=num_heads_window, num_heads_s=num_heads_stripe,
+                window_size=window_size, window_shift=i % 2 == 0, stripe_size=stripe_size, stripe_groups=stripe_groups,
+                stripe_type="H" if i % 2 == 0 else "W", stripe_shift=i % 4 in [2, 3] if stripe_shift else False,
+                mlp_ratio=mlp_ratio, qkv_bias=qkv_bias, qkv_proj_type=qkv_proj_type, anchor_proj_type=anchor_proj_type,
+                anchor_one_stage=anchor_one_stage, anchor_window_down_factor=anchor_window_down_factor, drop=drop,
+                attn_drop=attn_drop, drop_path=drop_path[i] if isinstance(drop_path, list) else drop_path,
+                norm_layer=norm_layer, pretrained_window_size=pretrained_window_size,
+                pretrained_stripe_size=pretrained_stripe_size, res_scale=0.1 if init_method == "r" else 1.0, args=args))
+            # fairscale_checkpoint / offload_to_cpu: activation checkpointing is a no-op for inference (grl.py:133)
+        self.conv = build_last_conv(conv_type, dim)
+        self._pack = _PackedConv()
+
+    def _init_weights(self):
+        """grl.py:138-162."""
+        for n, m in self.named_modules():
+            if self.init_method == "w":
+                if isinstance(m, (nn.Linear, nn.Conv2d)) and n.find("cpb_mlp") < 0:
+                    m.weight.data *= 0.1
+            elif self.init_method == "l":
+                if isinstance(m, nn.LayerNorm):
+                    nn.init.constant_(m.bias, 0)
+                    nn.init.constant_(m.weight, 0)
+            elif self.init_method.find("t") >= 0:
+                scale = 0.1 ** (len(self.init_method) - 1) * int(self.init_method[-1])
+                if isinstance(m, nn.Linear) and n.find("cpb_mlp") < 0:
+                    nn.init.trunc_normal_(m.weight, std=scale)
+                elif isinstance(m, nn.Conv2d):
+                    m.weight.data *= 0.1
+            else:
+                raise NotImplementedError(f"Parameter initialization method {self.init_method} not implemented in TransformerStage.")
+
+    @torch.no_grad()
+    def forward(self, x, x_size, table_index_mask):
+        res = x
+        for blk in self.blocks:
+            res = blk(res, x_size, table_index_mask)
+        B, L, C = x.shape
+        H, W = x_size
+        return conv2d_cl(self.conv, self._pack, res.view(B, H, W, C), res=x.view(B, H, W, C)).view(B, L, C)
+
+
+class GRL(nn.Module):
+    """models/networks/grl.py:176-569.  Same constructor kwargs (plus **kwargs swallowing the extra yaml keys),
+    parameter names and call contract as the reference network."""
+
+    def __init__(self, img_size=64, in_channels=3, out_channels=None, embed_dim=96, upscale=2, img_range=1.0,
+                 upsampler="", depths=[6, 6, 6, 6, 6, 6], num_heads_window=[3, 3, 3, 3, 3, 3],
+                 num_heads_stripe=[3, 3, 3, 3, 3, 3], window_size=8, stripe_size=[8, 8], stripe_groups=[None, None],
+                 stripe_shift=False, mlp_ratio=4.0, qkv_bias=True, qkv_proj_type="linear", anchor_proj_type="avgpool",
+                 anchor_one_stage=True, anchor_window_down_factor=1, out_proj_type="linear", local_connection=False,
+                 drop_rate=0.0, attn_drop_rate=0.0, drop_path_rate=0.1, norm_layer=nn.LayerNorm,
+                 pretrained_window_size=[0, 0], pretrained_stripe_size=[0, 0], conv_type="1conv", init_method="n",
+                 fairscale_checkpoint=False, offload_to_cpu=False, euclidean_dist=False, **kwargs):
+        super().__init__()
+        out_channels = out_channels or in_channels
+        self.in_channels, self.out_channels = in_channels, out_channels
+        num_out_feats = 64
+        self.embed_dim, self.upscale, self.upsampler, self.img_range = embed_dim, upscale, upsampler, img_range
+        if in_channels == 3:
+            self.mean = torch.Tensor((0.4488, 0.4371, 0.4040)).view(1, 3, 1, 1)
+        else:
+            self.mean = torch.zeros(1, 1, 1, 1)
+        stripe_size, stripe_groups = list(stripe_size), list(stripe_groups)
+        max_stripe_size = max([0 if s is None else s for s in stripe_size])
+        max_stripe_groups = max([0 if s is None else s for s in stripe_groups]) * anchor_window_down_factor
+        self.pad_size = max(window_size, max_stripe_size, max_stripe_groups)
+        self.input_resolution = to_2tuple(img_size)
+        self.window_size = to_2tuple(window_size)
+        self.shift_size = [w // 2 for w in self.window_size]
+        self.stripe_size, self.stripe_groups = stripe_size, stripe_groups
+        self.pretrained_window_size, self.pretrained_stripe_size = pretrained_window_size, pretrained_stripe_size
+        self.anchor_window_down_factor = anchor_window_down_factor
+        if out_proj_type != "linear":
+            raise NotImplementedError("only out_proj_type='linear' is on the B200 hot path")
+
+        self.conv_first = nn.Conv2d(in_channels, embed_dim, 3, 1, 1)
+        self.norm_start = norm_layer(embed_dim)
+        self.pos_drop = nn.Dropout(p=drop_rate)
+        dpr = [x.item() for x in torch.linspace(0, drop_path_rate, sum(depths))]
+        args = SimpleNamespace(out_proj_type=out_proj_type, local_connection=local_connection,
+                               euclidean_dist=euclidean_dist)
+        # Only the three coordinate tables are buffers (a few KB).  The reference also registers ~1.5 GB of int64
+        # indices and fp32 masks (grl.py:309-310); here those are closed forms inside the kernels.  The constructor
+        # still validates img_size like the reference does (ops.py:46 view error).
+        ss, _ = _get_stripe_info(self.stripe_size, self.stripe_groups, True, self.input_resolution)
+        for s, d in zip(list(ss) + list(self.window_size), list(self.input_resolution) * 2):
+            if s <= 0 or d % s != 0:
+                raise RuntimeError(f"img_size {self.input_resolution} is not a multiple of the window/stripe size {s}")
+        for k, v in self._tables(self.input_resolution).items():
+            self.register_buffer(k, v)
+
+        self.layers = nn.ModuleList()
+        for i in range(len(depths)):
+            self.layers.append(TransformerStage(
+                dim=embed_dim, input_resolution=self.input_resolution, depth=depths[i],
+                num_heads_window=num_heads_window[i], num_heads_stripe=num_heads_stripe[i],
+                window_size=self.window_size, stripe_size=stripe_size, stripe_groups=stripe_groups,
+                stripe_shift=stripe_shift, mlp_ratio=mlp_ratio, qkv_bias=qkv_bias, qkv_proj_type=qkv_proj_type,
+                anchor_proj_type=anchor_proj_type, anchor_one_stage=anchor_one_stage,
+                anchor_window_down_factor=anchor_window_down_factor, drop=drop_rate, attn_drop=attn_drop_rate,
+                drop_path=dpr[sum(depths[:i]): sum(depths[: i + 1])], norm_layer=norm_layer,
+                pretrained_window_size=pretrained_window_size, pretrained_stripe_size=pretrained_stripe_size,
+                conv_type=conv_type, init_method=init_method, fairscale_checkpoint=fairscale_checkpoint,
+                offload_to_cpu=offload_to_cpu, args=args))
+        self.norm_end = norm_layer(embed_dim)
+        self.conv_after_body = build_last_conv(conv_type, embed_dim)
+
+        if self.upsampler == "pixelshuffle":
+            self.conv_before_upsample = nn.Sequential(nn.Conv2d(embed_dim, num_out_feats, 3, 1, 1),
+                                                      nn.LeakyReLU(inplace=True))
+            self.upsample = Upsample(upscale, num_out_feats)
+            self.conv_last = nn.Conv2d(num_out_feats, out_channels, 3, 1, 1)
+        elif self.upsampler == "pixelshuffledirect":
+            self.upsample = UpsampleOneStep(upscale, embed_dim, out_channels)
+        elif self.upsampler == "nearest+conv":
+            assert self.upscale == 4, "only support x4 now."
+            self.conv_before_upsample = nn.Sequential(nn.Conv2d(embed_dim, num_out_feats, 3, 1, 1),
+                                                      nn.LeakyReLU(inplace=True))
+            self.conv_up1 = nn.Conv2d(num_out_feats, num_out_feats, 3, 1, 1)
+            self.conv_up2 = nn.Conv2d(num_out_feats, num_out_feats, 3, 1, 1)
+            self.conv_hr = nn.Conv2d(num_out_feats, num_out_feats, 3, 1, 1)
+            self.conv_last = nn.Conv2d(num_out_feats, out_channels, 3, 1, 1)
+            self.lrelu = nn.LeakyReLU(negative_slope=0.2, inplace=True)
+        else:
+            self.conv_last = nn.Conv2d(embed_dim, out_channels, 3, 1, 1)
+        self._packs = {}
+
+        self.apply(self._init_weights)
+        if init_method in ["l", "w"] or init_method.find("t") >= 0:
+            for layer in self.layers:
+                layer._init_weights()
+        # a full reference state_dict also carries index_*/mask_* buffers: drop them instead of failing strict loads
+        self._register_load_state_dict_pre_hook(self._drop_reference_buffers)
+
+    # ---- tables / indices / masks ------------------------------------------------------------
+    def _tables(self, x_size):
+        ss, _ = _get_stripe_info(self.stripe_size, self.stripe_groups, True, x_size)
+        df = self.anchor_window_down_factor
+        return {"table_w": G.coords_table(self.window_size), "table_sh": G.coords_table(ss, df),
+                "table_sv": G.coords_table(ss[::-1], df)}
+
+    def set_table_index_mask(self, x_size, materialize=False):
+        """grl.py:386-429.  With materialize=True returns the reference's 13 CPU tensors (bit-exact); the default
+        returns the three tables plus zero-size markers for the indices / masks the kernels compute on the fly."""
+        out = self._tables(x_size)
+        names_i = ("index_w", "index_sh_a2w", "index_sh_w2a", "index_sv_a2w", "index_sv_w2a")
+        names_m = ("mask_w", "mask_sh_a2w", "mask_sh_w2a", "mask_sv_a2w", "mask_sv_w2a")
+        if not materialize:
+            for n in names_i + names_m:
+                out[n] = _closed_form_marker()
+            return out
+        ss, sss = _get_stripe_info(self.stripe_size, self.stripe_groups, True, x_size)
+        df = self.anchor_window_down_factor
+        out["index_w"] = G.position_index(self.window_size)
+        out["mask_w"] = G.shift_mask(x_size, self.window_size, self.shift_size)
+        for d, s, sh in (("sh", ss, sss), ("sv", ss[::-1], sss[::-1])):
+            for tag, w2a in (("a2w", False), ("w2a", True)):
+                out[f"index_{d}_{tag}"] = G.position_index(s, df, w2a)
+                out[f"mask_{d}_{tag}"] = G.shift_mask(x_size, s, sh, df, w2a)
+        return out
+
+    def get_table_index_mask(self, device=None, input_resolution=None):
+        """grl.py:431-453 -- but a resolution change costs three small table uploads instead of a 1.3 GB rebuild."""
+        if tuple(input_resolution) == tuple(self.input_resolution):
+            t = {"table_w": self.table_w, "table_sh": self.table_sh, "table_sv": self.table_sv}
+        else:
+            t = {k: v.to(device) for k, v in self._tables(input_resolution).items()}
+        for n in ("index_w", "index_sh_a2w", "index_sh_w2a", "index_sv_a2w", "index_sv_w2a", "mask_w", "mask_sh_a2w",
+                  "mask_sh_w2a", "mask_sv_a2w", "mask_sv_w2a"):
+            t[n] = _closed_form_marker()
+        return t
+
+    @staticmethod
+    def _drop_reference_buffers(state_dict, prefix, *args):
+        for k in list(state_dict.keys()):
+            n = k[len(prefix):] if k.startswith(prefix) else None
+            if n is not None and "." not in n and (n.startswith("index_") or n.startswith("mask_")):
+                state_dict.pop(k)
+
+    def _init_weights(self, m):
+        """grl.py:455-462."""
+        if isinstance(m, nn.Linear):
+            nn.init.trunc_normal_(m.weight, std=0.02)
+            if m.bias is not None:
+                nn.init.constant_(m.bias, 0)
+        elif isinstance(m, nn.LayerNorm):
+            nn.init.constant_(m.bias, 0)
+            nn.init.constant_(m.weight, 1.0)
+
+    @torch.jit.ignore
+    def no_weight_decay(self):
+        return {"absolute_pos_embed"}
+
+    @torch.jit.ignore
+    def no_weight_decay_keywords(self):
+        return {"relative_position_bias_table"}
+
+    # ---- forward --------------------------------------------------------------------------------
+    def check_image_size(self, x):
+        """grl.py:479-489."""
+        _, _, h, w = x.size()
+        mod_pad_h = (self.pad_size - h % self.pad_size) % self.pad_size
+        mod_pad_w = (self.pad_size - w % self.pad_size) % self.pad_size
+        try:
+            x = F.pad(x, (0, mod_pad_w, 0, mod_pad_h), "reflect")
+        except BaseException:
+            x = F.pad(x, (0, mod_pad_w, 0, mod_pad_h), "constant")
+        return x
+
+    def _conv(self, name, conv, x, act=K.ACT_NONE, slope=0.0, res=None):
+        pack = self._packs.setdefault(name, _PackedConv())
+        return conv2d_cl(conv, pack, x, act, slope, res)
+
+    @torch.no_grad()
+    def _features_cl(self, x):
+        """x (B, H, W, C) channels-last -> same; grl.py:491-504 without the layout round trips."""
+        B, H, W, C = x.shape
+        x_size = (H, W)
+        t = x.view(B, H * W, C)
+        t = K.ln_residual(None, t, self.norm_start.weight, self.norm_start.bias, self.norm_start.eps)
+        tim = self.get_table_index_mask(x.device, x_size)
+        for layer in self.layers:
+            t = layer(t, x_size, tim)
+        t = K.ln_residual(None, t, self.norm_end.weight, self.norm_end.bias, self.norm_end.eps)
+        return t.view(B, H, W, C)
+
+    def forward_features(self, x):
+        """(B, C, H, W) -> (B, C, H, W) like the reference."""
+        K.capi.require_device(x)
+        return self._features_cl(x.permute(0, 2, 3, 1).contiguous()).permute(0, 3, 1, 2)
+
+    @torch.no_grad()
+    def forward(self, x):
+        K.capi.require_device(x)
+        H, W = x.shape[2:]
+        x = self.check_image_size(x)
+        self.mean = self.mean.type_as(x)
+        x = ((x - self.mean) * self.img_range).float()
+        xc = x.permute(0, 2, 3, 1).contiguous()  # channels-last from here on
+        first = self._conv("conv_first", self.conv_first, xc)
+        body = self._conv("conv_after_body", self.conv_after_body, self._features_cl(first), res=first)
+        if self.upsampler == "pixelshuffle":
+            t = self._conv("conv_before_upsample", self.conv_before_upsample[0], body, K.ACT_LEAKY, 0.01)
+            y = self._conv("conv_last", self.conv_last, self.upsample.forward_cl(t))
+        elif self.upsampler == "pixelshuffledirect":
+            y = self.upsample.forward_cl(body)
+        elif self.upsampler == "nearest+conv":
+            t = self._conv("conv_before_upsample", self.conv_before_upsample[0], body, K.ACT_LEAKY, 0.01)
+            up = lambda v: v.repeat_interleave(2, dim=1).repeat_interleave(2, dim=2)
+            t = self._conv("conv_up1", self.conv_up1, up(t), K.ACT_LEAKY, 0.2)
+            t = self._conv("conv_up2", self.conv_up2, up(t), K.ACT_LEAKY, 0.2)
+            y = self._conv("conv_last", self.conv_last, self._conv("conv_hr", self.conv_hr, t, K.ACT_LEAKY, 0.2))
+        else:
+            if self.in_channels == self.out_channels:
+                y = self._conv("conv_last", self.conv_last, body, res=xc)
+            else:
+                y = self._conv("conv_last", self.conv_last, body)
+        y = y.permute(0, 3, 1, 2) / self.img_range + self.mean
+        return y[:, :, : H * self.upscale, : W * self.upscale].contiguous()
+
+    def flops(self):
+        pass
+
+    def convert_checkpoint(self, state_dict):
+        """grl.py:556-569."""
+        for k in list(state_dict.keys()):
+            if (k.find("relative_coords_table") >= 0 or k.find("relative_position_index") >= 0
+                    or k.find("attn_mask") >= 0 or k.find("model.table_") >= 0 or k.find("model.index_") >= 0
+                    or k.find("model.mask_") >= 0):
+                state_dict.pop(k)
+                print(k)
+        return state_dict

@@ -1,0 +1,126 @@
+/* grl_b200.h -- C ABI of libgrl_b200.so: the B200 (sm_100a) implementation of GRL's forward hot path.
+ *
+ * The reference (ofsoundof/GRL-Image-Restoration) is pure Python/ATen: it has no FFI, plugin or
+ * operator registry for this path.  Its boundary is the nn.Module contract;
+ * every entry point below therefore cites the reference *Python interface* it replaces
+ * (paths relative to the reference root) and INTEGRATION.md shows the ctypes binding a maintainer
+ * adds.  Conventions for every function:
+ *   - plain pointers + sizes only; all data pointers are DEVICE pointers unless the name ends in
+ *     _host; `stream` is a cudaStream_t passed as void*;
+ *   - no allocation, no synchronisation, no global mutable state besides the per-thread error
+ *     string; re-entrant per stream;
+ *   - returns 0 on success, a negative GrlStatus otherwise; grl_last_error() gives the message
+ *     (the Python wrappers raise RuntimeError -- same behaviour as a failing ATen call).
+ * Activations are channels-last: a (B, L, C) token tensor is the same memory as (B, H, W, C).
+ */
+#ifndef GRL_B200_H_
+#define GRL_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GRL_B200_ABI_VERSION 1
+
+typedef enum {
+  GRL_OK = 0,
+  GRL_ERR_INVALID = -1,   /* bad argument / unsupported shape */
+  GRL_ERR_CUDA = -2,      /* a CUDA runtime/driver call failed */
+  GRL_ERR_WORKSPACE = -3, /* workspace too small */
+  GRL_ERR_ARCH = -4       /* device is not sm_100 */
+} GrlStatus;
+
+typedef enum { GRL_ACT_NONE = 0, GRL_ACT_GELU = 1, GRL_ACT_LEAKY = 2 } GrlAct;
+
+/* One attention "level": a (H x W) token grid cut into (wh x ww) windows/stripes after a cyclic
+ * roll by (-sh, -sw)  [torch.roll + window_partition: mixed_attn_block_efficient.py:139-147,
+ * :234-247; models/common/ops.py:36-54]. */
+typedef struct {
+  int32_t H, W;   /* grid size (tokens, or anchors = tokens / df) */
+  int32_t wh, ww; /* window / stripe size on this grid */
+  int32_t sh, sw; /* cyclic shift on this grid (0 = none) */
+} GrlGrid;
+
+const char* grl_last_error(void);
+int grl_abi_version(void);
+/* 1 if the current device is compute capability 10.x */
+int grl_device_ok(void);
+
+/* ---- geometry, host side (bit-exact restatement of models/common/ops.py; used by tests and by the
+ * Python surface to honour the reference's table/index/mask arguments) ------------------------- */
+/* get_relative_position_index_simple (ops.py:352-375): out is (n1, n2) int64, row-major.
+ * window_to_anchor != 0: n1 = wh*ww, n2 = (wh/df)*(ww/df); else transposed roles. */
+int grl_rel_index_host(int wh, int ww, int df, int window_to_anchor, int64_t* out);
+/* calculate_mask / calculate_mask_all (ops.py:112-157): out is (nW, n1, n2) fp32 of 0 / -100. */
+int grl_shift_mask_host(int H, int W, int wh, int ww, int sh, int sw, int df, int window_to_anchor, float* out);
+/* get_relative_coords_table_all (ops.py:225-271), pretrained size 0: out is ((wh+awh-1)*(ww+aww-1), 2) fp32 */
+int grl_coords_table_host(int wh, int ww, int df, float* out);
+
+/* ---- fp32 operators (exact-parity path; every one is a hand-written sm_100a kernel) ---------- */
+
+/* AffineTransform bias: out[h, r] = 16*sigmoid(CPB_MLP(table[r]))  for r < rows
+ * (mixed_attn_block_efficient.py:41-47 with the gather commuted out; mixed_attn_block.py:24-31).
+ * table (rows,2); w1 (hidden,2); b1 (hidden); w2 (heads,hidden); out (heads, rows). */
+int grl_bias_table_f32(const float* table, int rows, const float* w1, const float* b1, const float* w2,
+                       int hidden, int heads, float* out, void* stream);
+
+/* AffineTransform.forward on a materialised map (mixed_attn_block_efficient.py:36-58):
+ * attn (B_, heads, n1, n2) in place: attn*exp(min(logit_scale,ln100)) + bias[h, index[i,j]] + mask[b_%nW,i,j].
+ * bias = output of grl_bias_table_f32; index (n1,n2) int64; mask (nW,n1,n2) or NULL. */
+int grl_affine_f32(float* attn, int64_t B_, int heads, int n1, int n2, const float* logit_scale,
+                   const float* bias, int rows, const int64_t* index, const float* mask, int nW, void* stream);
+
+/* y[m, n] = act(sum_k x[m*ldx + k] * w[n*K + k] + b[n]) (+ res[m*ldr + n]);  nn.Linear / QKVProjection /
+ * AnchorLinear.reduction / Mlp.fc1,fc2 / MixedAttention.proj (mixed_attn_block.py:661-676,:714-736;
+ * swin_v1_block.py:37-43; mixed_attn_block_efficient.py:379). b, res may be NULL. */
+int grl_linear_f32(const float* x, int64_t ldx, const float* w, const float* b, const float* res, int64_t ldr,
+                   float* y, int64_t ldy, int64_t M, int N, int K, int act, float slope, void* stream);
+
+/* 3x3 / stride 1 / pad 1 convolution on channels-last data (nn.Conv2d in CAB mixed_attn_block.py:973-977,
+ * TransformerStage.conv grl.py:136,:168, conv_first / conv_after_body / upsampler heads grl.py:293,:348-379).
+ * x (B,H,W,Cin); w packed (Cout, 9*Cin) with k = (ky*3+kx)*Cin + c; y (B,H,W,Cout); res optional (B,H,W,Cout). */
+int grl_conv3x3_f32(const float* x, const float* w, const float* b, const float* res, float* y, int B, int H, int W,
+                    int Cin, int Cout, int act, float slope, void* stream);
+
+/* AvgPool2d(df, df) on channels-last data (AnchorLinear.pooling, mixed_attn_block.py:725,:733). */
+int grl_avgpool_f32(const float* x, float* y, int B, int H, int W, int C, int df, void* stream);
+
+/* out = (x ? x : 0) + res_scale * LayerNorm(u; gamma, beta, eps) (+ cab_y * cab_gate[b, c])
+ * (post-norm residual, mixed_attn_block_efficient.py:543-554; norm_start/norm_end grl.py:494,:501 with x = NULL).
+ * Rows M = B*L; cab_y (M,C) and cab_gate (B,C) optional (both or none). */
+int grl_ln_residual_f32(const float* x, const float* u, const float* gamma, const float* beta, float eps,
+                        float res_scale, const float* cab_y, const float* cab_gate, int64_t L, float* out,
+                        int64_t M, int C, void* stream);
+
+/* ChannelAttention gate (mixed_attn_block.py:948-967): gate[b,c] = sigmoid(W2 relu(W1 mean_L(y[b]) + b1) + b2).
+ * y (B,L,C); w1 (R,C); w2 (C,R); workspace >= grl_channel_gate_workspace(B,L,C) bytes. */
+size_t grl_channel_gate_workspace(int B, int64_t L, int C);
+int grl_channel_gate_f32(const float* y, int B, int64_t L, int C, const float* w1, const float* b1, const float* w2,
+                         const float* b2, int R, float* gate, void* workspace, size_t workspace_bytes, void* stream);
+
+/* WindowAttention.forward (mixed_attn_block_efficient.py:128-165) fused: roll + partition + cosine attention
+ * + learned scale + relative-position bias + shift mask + softmax + AV + merge + reverse roll.
+ * qkv: token rows of `ld_qkv` floats; the window half starts at qkv and is laid out (3, heads, d).
+ * out: token rows of `ld_out` floats, channel = head*d + e.  bias (heads, rows) from grl_bias_table_f32 with
+ * rows = (2wh-1)(2ww-1).  use_mask: apply the region-id shift mask (mask argument not None in the reference). */
+int grl_window_attn_f32(const float* qkv, int64_t ld_qkv, float* out, int64_t ld_out, int B, GrlGrid grid, int heads,
+                        int d, const float* logit_scale, const float* bias, int use_mask, void* stream);
+
+/* AnchorStripeAttention.forward (mixed_attn_block_efficient.py:215-270) fused: two chained attentions
+ * X1 = softmax(a k^T) v (anchors attend to the stripe), Y = softmax(q a^T) X1.
+ * qkv: stripe half (3, heads, d) per token; anchor (B, H/df, W/df, heads*d) rows of `ld_anchor` floats;
+ * tok = stripe grid on tokens, anc = the same stripes on the anchor grid; bias1/scale1 = attn_transform1
+ * (a2w index), bias2/scale2 = attn_transform2 (w2a index).  workspace >= grl_stripe_attn_workspace bytes. */
+size_t grl_stripe_attn_workspace(int B, GrlGrid tok, GrlGrid anc, int heads, int d);
+int grl_stripe_attn_f32(const float* qkv, int64_t ld_qkv, const float* anchor, int64_t ld_anchor, float* out,
+                        int64_t ld_out, int B, GrlGrid tok, GrlGrid anc, int heads, int d, const float* logit_scale1,
+                        const float* bias1, const float* logit_scale2, const float* bias2, int use_mask,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GRL_B200_H_ */

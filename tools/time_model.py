@@ -1,0 +1,44 @@
+"""Dev tool: time GRL.forward for a named config on cuda:0 (CUDA events)."""
+import argparse
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+from _pkgload import load_package  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--variant", default="base")
+ap.add_argument("--task", default="sr")
+ap.add_argument("--scale", type=int, default=4)
+ap.add_argument("--size", type=int, default=256)
+ap.add_argument("--batch", type=int, default=1)
+ap.add_argument("--iters", type=int, default=3)
+ap.add_argument("--precision", default=None)
+a = ap.parse_args()
+pkg = load_package()
+import grl_oracle as orc  # noqa: E402  (weights only)
+
+cfg = pkg.configs.grl_config(a.variant, a.task, a.scale, a.size)
+m = pkg.GRL(**cfg)
+m.load_state_dict(orc.synth_state_dict(cfg, 0), strict=False)
+m = m.cuda().eval()
+if a.precision is not None and hasattr(m, "set_precision"):
+    m.set_precision(a.precision)
+x = torch.rand(a.batch, 3, a.size, a.size, device="cuda")
+m(x)
+torch.cuda.synchronize()
+ts = []
+for _ in range(a.iters):
+    e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+    e0.record()
+    y = m(x)
+    e1.record()
+    torch.cuda.synchronize()
+    ts.append(e0.elapsed_time(e1))
+ms = sorted(ts)[len(ts) // 2]
+print(f"{a.variant}/{a.task} x{a.scale} {a.size}^2 B={a.batch} prec={a.precision}: {ms:.1f} ms/forward, "
+      f"{a.batch * a.size * a.size / 1e6 / (ms / 1e3):.4f} Mpix/s, peak mem {torch.cuda.max_memory_allocated() / 2**30:.2f} GiB")
