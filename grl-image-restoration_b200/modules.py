@@ -141,6 +141,8 @@ class AnchorStripeAttention(nn.Module):
 
     def grids(self, x_size):
         ss, sh = _get_stripe_info(self.stripe_size, self.stripe_groups, self.stripe_shift, x_size)
+        if not self.stripe_shift:  # with stripe_groups the info carries a shift even for unshifted blocks, but
+            sh = [0, 0]            # the roll itself is guarded by stripe_shift (efficient.py:235)
         df = self.anchor_window_down_factor
         return G.token_grid(x_size, ss, sh), G.anchor_grid(x_size, ss, sh, df)
 

@@ -125,7 +125,7 @@ def test_window_attention(pkg, oracle, device, B, H, W, ws, heads, d, shifted):
 STRIPE_CASES = [  # (B, H, W, stripe, groups, df, heads, d, shifted)
     (2, 16, 32, [8, 16], [None, None], 2, 2, 9, True), (1, 16, 32, [16, 8], [None, None], 2, 2, 9, False),
     (1, 64, 64, [64, 64], [None, None], 4, 2, 16, True), (1, 32, 32, [4, None], [None, 2], 2, 2, 8, True),
-    (1, 32, 32, [None, 8], [1, None], 2, 2, 8, True), (1, 24, 24, [6, 12], [None, None], 3, 1, 32, True),
+    (1, 32, 32, [None, 8], [1, None], 2, 2, 8, True), (1, 16, 16, [4, None], [None, 2], 2, 2, 8, False), (1, 24, 24, [6, 12], [None, None], 3, 1, 32, True),
     (1, 64, 128, [64, 128], [None, None], 2, 3, 30, True), (1, 48, 96, [48, 96], [None, None], 4, 3, 30, True),
 ]
 
