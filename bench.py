@@ -1,0 +1,287 @@
+"""bench.py -- BASELINE.json's metric: Mpix/s of GRL-Base x4 SR on 256x256 tiles (released hyper-parameters:
+window 32, stripes 64x64, df 2, CAB on, pixelshuffle head), batch-sharded, 16 tiles per GPU (weak scaling).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # our arm (one process per GPU under torchrun)
+    python bench.py --impl reference [--gpus N] [--steps K] ...    # the reference's CPU PyTorch path (oracle port)
+
+One "step" = one forward of the hot path over one batch of synthetic tiles.  Prints ONE JSON line (rank 0).
+`value` is device-resident throughput; `e2e` goes through the public nn.Module call with pinned HOST buffers
+(H2D of inputs + ground truth, forward, reference PSNR on the device, D2H of the per-image PSNR) and ends with the
+only collective this path has -- the all-gather of (index, psnr) pairs (NCCL).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (variant, task, scale, tile, tiles per GPU)
+    "cfg4": ("base", "sr", 4, 256, 16),  # the configuration the metric is quoted on (16 of the 128 tiles per GPU)
+    "cfg2": ("small", "sr", 4, 256, 16),
+    "cfg3": ("base", "dn", 1, 256, 8),
+    "cfg1": ("tiny", "sr", 2, 64, 1),
+}
+CPU_SAMPLE_TILE = 64  # cpu legs run ONE 64x64 tile of the same network per step (same per-pixel attention structure)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return dict(tflops=d.get("bf16_tflops_sustained", 1447.6), hbm=d.get("hbm_gbs", 6574.8), src="measured")
+    return dict(tflops=1400.0, hbm=6650.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "200"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=lambda: [self.rows.append(l) for l in self.proc.stdout], daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for l in self.rows:
+            f = [t.strip() for t in l.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])), mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=sorted(reasons), samples=len(sm))
+
+
+def cpu_leg(cfg_tuple, steps, warmup):
+    """The reference's own CPU implementation of the path, restated in oracle/grl_oracle.py (kind "port": the
+    reference is Python and cannot travel to the GPU box), fp32, all host threads, one 64x64 tile per step."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import grl_oracle as orc
+    from _pkgload import load_package
+
+    pkg = load_package()
+    variant, task, scale, tile, _ = cfg_tuple
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = pkg.configs.grl_config(variant, task, scale, CPU_SAMPLE_TILE)
+    sd = orc.synth_state_dict(cfg, seed=0)
+    x = orc.synth_input((1, 3, CPU_SAMPLE_TILE, CPU_SAMPLE_TILE), seed=1234)
+    ts, y = [], None
+    with torch.no_grad():
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            y = orc.grl_forward(sd, cfg, x)
+            if i >= warmup:
+                ts.append(time.perf_counter() - t0)
+    sec = sum(ts) / len(ts)
+    return dict(value=CPU_SAMPLE_TILE * CPU_SAMPLE_TILE / 1e6 / sec, sec_per_step=sec, cores=cores, cfg=cfg, sd=sd, x=x,
+                y=y, sample=f"1 tile of {CPU_SAMPLE_TILE}x{CPU_SAMPLE_TILE} px of the same network per step "
+                            f"({steps} timed, {warmup} warm-up)")
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg4", choices=sorted(WORKLOADS))
+    ap.add_argument("--tiles-per-gpu", type=int, default=None)
+    ap.add_argument("--precision", default="auto", choices=["auto", "fp32", "bf16"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    a = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    variant, task, scale, tile, per_gpu = WORKLOADS[a.workload]
+    if a.tiles_per_gpu:
+        per_gpu = a.tiles_per_gpu
+    W = max(a.warmup, 0)
+    metric = "Mpix/s (input pixels) GRL-Base x4 SR 256x256 tiles" if a.workload == "cfg4" else f"Mpix/s {a.workload}"
+    cfg_desc = dict(workload=f"{a.workload}: GRL-{variant} {task} x{scale}, {tile}x{tile} synthetic tiles, released "
+                             f"hyper-parameters", tiles_per_gpu=per_gpu, global_batch=per_gpu * world, tile=tile,
+                    parallelism=f"batch-sharded dp{world}, weights replicated",
+                    l2="per-step working set (GBs of activations) >> 126 MB L2; no explicit flush needed")
+
+    # ------------------------------------------------------------------ reference arm (CPU, rank 0 only)
+    if a.impl == "reference":
+        if rank != 0:
+            return
+        r = cpu_leg(WORKLOADS[a.workload], max(a.steps, 1), W)
+        print(json.dumps({
+            "impl": "reference", "metric": metric, "value": r["value"], "unit": "Mpix/s", "n_gpus": a.gpus,
+            "steps": a.steps, "warmup": W, "ms_per_step": r["sec_per_step"] * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg_desc,
+            "cpu_baseline": {"value": r["value"], "unit": "Mpix/s", "cores": r["cores"], "kind": "port",
+                             "sample": r["sample"]},
+            "e2e": {"value": r["value"], "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        }))
+        return
+
+    # ------------------------------------------------------------------ our arm
+    import torch.distributed as dist
+    from _pkgload import load_package
+
+    pkg = load_package()
+    from grl_image_restoration_b200 import capi, flops, functional as K, metrics, sharding
+
+    assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback for the product path)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import grl_oracle as orc  # synthetic weights/inputs shared with the checker; not on the timed path
+
+    cfg = pkg.configs.grl_config(variant, task, scale, tile)
+    model = pkg.GRL(**cfg)
+    model.load_state_dict(orc.synth_state_dict(cfg, seed=0), strict=False)
+    model = model.to(dev).eval()
+    precision = a.precision
+    if hasattr(model, "set_precision"):
+        precision = model.set_precision(a.precision)
+    else:
+        precision = "fp32"
+    lo, hi = sharding.shard_range(per_gpu * world, rank, world)
+    g = torch.Generator().manual_seed(1234 + rank)
+    x_host = torch.rand(hi - lo, 3, tile, tile, generator=g).pin_memory()
+    gt_host = torch.rand(hi - lo, 3, tile * scale, tile * scale, generator=g).pin_memory()
+    x_dev = x_host.to(dev)
+    idx = torch.arange(lo, hi, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput
+    for _ in range(max(W, 3)):
+        y = model(x_dev)
+    barrier()
+    launches0 = capi.lib().grl_launch_count()
+    K.timer = K.KernelTimer()
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+    smi_index = vis.split(",")[local_rank] if vis and all(v.strip().isdigit() for v in vis.split(",")) else local_rank
+    sampler = ClockSampler(smi_index)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(a.steps):
+        y = model(x_dev)
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    ms_total = e0.elapsed_time(e1)
+    attn_ms = K.timer.totals_ms()
+    K.timer = None
+    launches = capi.lib().grl_launch_count() - launches0
+    t = torch.tensor([ms_total], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = t.item() / a.steps
+    mpix_step = per_gpu * world * tile * tile / 1e6
+    value = mpix_step / (ms_step / 1e3)
+
+    # ---- end to end through the public API with host buffers (+ the final metric all-gather)
+    def e2e_step():
+        xd = x_host.to(dev, non_blocking=True)
+        gd = gt_host.to(dev, non_blocking=True)
+        out = model(xd)
+        p = metrics.psnr(out, gd, border=scale if scale > 1 else 0)
+        gv, gi = sharding.gather_metric(p, idx)
+        return gv.cpu(), gi.cpu()
+
+    e2e_step()
+    barrier()
+    e0.record()
+    for _ in range(a.steps):
+        pv, pi = e2e_step()
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = mpix_step / (t.item() / a.steps / 1e3)
+    mean_psnr = sharding.average_metric(pv, pi)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernels (the fused attention kernels), live CUDA-event timings
+    pk = peaks()
+    counts = flops.attention_counts(cfg, (tile, tile))
+    attn_total_ms = sum(v[0] for v in attn_ms.values())
+    attn_launches = sum(v[1] for v in attn_ms.values())
+    flops_timed = counts["f_attn"] * (hi - lo) * a.steps  # this rank's images
+    achieved = flops_timed / (attn_total_ms / 1e3) / 1e12 if attn_total_ms > 0 else 0.0
+    roof = {"bound": "tensor", "kernel": "fused window + anchored-stripe attention (QK^T + PV)",
+            "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tflops"],
+            "peak_source": f"bf16 sustained, {pk['src']}", "traffic": None,
+            "share_of_step": attn_total_ms / ms_total, "launches_timed": attn_launches,
+            "algorithmic_gflop_per_image": counts["f_attn"] / 1e9, "qk_frac": achieved / 2 / pk["tflops"],
+            "whole_model_tflops": None}
+
+    out = {"metric": metric, "value": value, "unit": "Mpix/s", "n_gpus": world, "steps": a.steps, "warmup": max(W, 3),
+           "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "f32" if precision == "fp32" else "bf16", "data": "synthetic", "config": cfg_desc,
+           "output_mpix_per_s": value * scale * scale, "clocks": clocks, "gpu_launches": int(launches),
+           "e2e": {"value": e2e_value, "unit": "Mpix/s", "h2d_bytes_per_step": int(x_host.numel() * 4 + gt_host.numel() * 4),
+                   "d2h_bytes_per_step": int(pv.numel() * 4 + pi.numel() * 8),
+                   "includes": "H2D inputs+GT from pinned memory, forward, reference PSNR on device, all-gather, D2H"},
+           "mean_psnr_vs_random_gt_db": mean_psnr, "roofline": roof}
+
+    # ---- CPU baseline (rank 0, N=1 only) + PSNR of our output against the reference path on the same sample
+    if world == 1 and not a.no_cpu_baseline:
+        r = cpu_leg(WORKLOADS[a.workload], 2, 1)
+        out["cpu_baseline"] = {"value": r["value"], "unit": "Mpix/s", "cores": r["cores"], "kind": "port",
+                               "sample": r["sample"]}
+        small = pkg.GRL(**r["cfg"])
+        small.load_state_dict(r["sd"], strict=False)
+        small = small.to(dev).eval()
+        if hasattr(small, "set_precision"):
+            small.set_precision(a.precision)
+        yc = small(r["x"].to(dev)).cpu()
+        gt = torch.rand(yc.shape, generator=torch.Generator().manual_seed(7))
+        b = scale if scale > 1 else 0
+        out["parity"] = {"max_abs_vs_reference_path": (yc - r["y"]).abs().max().item(),
+                         "psnr_cand_vs_reference_db": orc.psnr(yc, r["y"], b).mean().item(),
+                         "delta_psnr_vs_gt_db": abs(orc.psnr(yc, gt, b).mean().item() - orc.psnr(r["y"], gt, b).mean().item()),
+                         "sample": f"one {CPU_SAMPLE_TILE}x{CPU_SAMPLE_TILE} tile, same weights, reference CPU path"}
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

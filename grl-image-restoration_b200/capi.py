@@ -29,6 +29,7 @@ _SIGNATURES = {
     "grl_last_error": (ctypes.c_char_p, []),
     "grl_abi_version": (c_int, []),
     "grl_device_ok": (c_int, []),
+    "grl_launch_count": (ctypes.c_uint64, []),
     "grl_rel_index_host": (c_int, [c_int, c_int, c_int, c_int, c_vp]),
     "grl_shift_mask_host": (c_int, [c_int] * 8 + [c_vp]),
     "grl_coords_table_host": (c_int, [c_int, c_int, c_int, c_vp]),

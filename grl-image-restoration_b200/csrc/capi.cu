@@ -10,6 +10,10 @@ char* error_buffer() {
   static thread_local char buf[512] = {0};
   return buf;
 }
+unsigned long long& launch_counter() {
+  static unsigned long long n = 0;
+  return n;
+}
 }  // namespace grl
 
 using namespace grl;
@@ -18,6 +22,7 @@ extern "C" {
 
 const char* grl_last_error(void) { return error_buffer(); }
 int grl_abi_version(void) { return GRL_B200_ABI_VERSION; }
+uint64_t grl_launch_count(void) { return launch_counter(); }
 
 int grl_device_ok(void) {
   int dev = 0, major = 0;

@@ -10,6 +10,7 @@
 namespace grl {
 
 char* error_buffer();  // thread-local, defined in capi.cu
+unsigned long long& launch_counter();  // kernels launched by this library since load (defined in capi.cu)
 
 inline int fail(int code, const char* fmt, ...) {
   va_list ap;
@@ -34,6 +35,7 @@ inline int fail(int code, const char* fmt, ...) {
 
 #define GRL_LAUNCH_CHECK(name)                                                                        \
   do {                                                                                                \
+    ++::grl::launch_counter();                                                                        \
     cudaError_t e__ = cudaGetLastError();                                                             \
     if (e__ != cudaSuccess)                                                                           \
       return ::grl::fail(GRL_ERR_CUDA, "launch of %s failed: %s", name, cudaGetErrorString(e__));      \

@@ -9,6 +9,33 @@ from . import capi
 ACT_NONE, ACT_GELU, ACT_LEAKY = 0, 1, 2
 
 
+class KernelTimer:
+    """Optional CUDA-event timer around the attention launches (bench.py's roofline leg).  Events are recorded on
+    the stream the kernels are launched on (torch's current stream)."""
+
+    def __init__(self):
+        self.pairs = {}
+
+    def wrap(self, tag, fn):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = fn()
+        e1.record()
+        self.pairs.setdefault(tag, []).append((e0, e1))
+        return out
+
+    def totals_ms(self):
+        """{tag: (total ms, launches)} -- call after a synchronize."""
+        return {k: (sum(a.elapsed_time(b) for a, b in v), len(v)) for k, v in self.pairs.items()}
+
+
+timer = None  # set to a KernelTimer to time attention kernels
+
+
+def _timed(tag, fn):
+    return fn() if timer is None else timer.wrap(tag, fn)
+
+
 def _f32c(t, name):
     capi.require_device(t)
     if t.dtype != torch.float32:
@@ -120,9 +147,9 @@ def window_attention(qkv, B, grid, heads, logit_scale, bias, use_mask, out=None)
     if out is None:
         out = torch.empty(B, qkv.shape[1], c, device=qkv.device, dtype=torch.float32)
     op, ldo = _token_rows(out, "out")
-    capi.check(capi.lib().grl_window_attn_f32(qp, ldq, op, ldo, B, grid, heads, c // heads,
-                                              capi.ptr(logit_scale.reshape(-1)), capi.ptr(bias), int(use_mask),
-                                              capi.stream()))
+    _timed("window_attn", lambda: capi.check(capi.lib().grl_window_attn_f32(
+        qp, ldq, op, ldo, B, grid, heads, c // heads, capi.ptr(logit_scale.reshape(-1)), capi.ptr(bias),
+        int(use_mask), capi.stream())))
     return out
 
 
@@ -137,8 +164,8 @@ def stripe_attention(qkv, anchor, B, tok_grid, anc_grid, heads, scale1, bias1, s
     d = c // heads
     nbytes = capi.lib().grl_stripe_attn_workspace(B, tok_grid, anc_grid, heads, d)
     ws = torch.empty(max(nbytes, 4) // 4, device=qkv.device, dtype=torch.float32)
-    capi.check(capi.lib().grl_stripe_attn_f32(qp, ldq, capi.ptr(anchor), c, op, ldo, B, tok_grid, anc_grid, heads, d,
-                                              capi.ptr(scale1.reshape(-1)), capi.ptr(bias1),
-                                              capi.ptr(scale2.reshape(-1)), capi.ptr(bias2), int(use_mask),
-                                              capi.ptr(ws), nbytes, capi.stream()))
+    _timed("stripe_attn", lambda: capi.check(capi.lib().grl_stripe_attn_f32(
+        qp, ldq, capi.ptr(anchor), c, op, ldo, B, tok_grid, anc_grid, heads, d, capi.ptr(scale1.reshape(-1)),
+        capi.ptr(bias1), capi.ptr(scale2.reshape(-1)), capi.ptr(bias2), int(use_mask), capi.ptr(ws), nbytes,
+        capi.stream())))
     return out

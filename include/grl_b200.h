@@ -46,6 +46,8 @@ typedef struct {
 
 const char* grl_last_error(void);
 int grl_abi_version(void);
+/* number of kernels this library has launched since it was loaded (bench.py's gpu_launches) */
+uint64_t grl_launch_count(void);
 /* 1 if the current device is compute capability 10.x */
 int grl_device_ok(void);
 
