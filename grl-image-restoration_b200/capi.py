@@ -25,6 +25,24 @@ def grid(H, W, wh, ww, sh=0, sw=0):
     return GrlGrid(int(H), int(W), int(wh), int(ww), int(sh), int(sw))
 
 
+class GrlTcGemm(ctypes.Structure):
+    _fields_ = [("x", c_vp), ("w", c_vp), ("bias", c_vp), ("M", c_i64), ("B", ctypes.c_int32), ("H", ctypes.c_int32),
+                ("W", ctypes.c_int32), ("kpad", ctypes.c_int32), ("npad", ctypes.c_int32), ("taps", ctypes.c_int32),
+                ("epi", ctypes.c_int32), ("n_store", ctypes.c_int32), ("n_real", ctypes.c_int32), ("out_bf16", c_vp),
+                ("ldo_bf16", c_i64), ("out_f32", c_vp), ("ldo_f32", c_i64), ("res_f32", c_vp), ("ldr", c_i64),
+                ("act", ctypes.c_int32), ("slope", c_f32), ("slot_scale", c_vp), ("C", ctypes.c_int32), ("gamma", c_vp),
+                ("beta", c_vp), ("eps", c_f32), ("res_scale", c_f32), ("cab_y", c_vp), ("ld_caby", c_i64),
+                ("cab_gate", c_vp), ("L", c_i64)]
+
+
+class GrlTcAttn(ctypes.Structure):
+    _fields_ = [("gq", GrlGrid), ("gk", GrlGrid), ("q", c_vp), ("ldq", c_i64), ("q_off", ctypes.c_int32), ("k", c_vp),
+                ("ldk", c_i64), ("k_off", ctypes.c_int32), ("v", c_vp), ("ldv", c_i64), ("v_off", ctypes.c_int32),
+                ("v_dense", ctypes.c_int32), ("out", c_vp), ("ldo", c_i64), ("o_off", ctypes.c_int32),
+                ("o_dense", ctypes.c_int32), ("B", ctypes.c_int32), ("heads", ctypes.c_int32), ("bias", c_vp),
+                ("rows", ctypes.c_int32), ("use_mask", ctypes.c_int32)]
+
+
 _SIGNATURES = {
     "grl_last_error": (ctypes.c_char_p, []),
     "grl_abi_version": (c_int, []),
@@ -34,6 +52,15 @@ _SIGNATURES = {
     "grl_shift_mask_host": (c_int, [c_int] * 8 + [c_vp]),
     "grl_coords_table_host": (c_int, [c_int, c_int, c_int, c_vp]),
     "grl_bias_table_f32": (c_int, [c_vp, c_int, c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_vp]),
+    "grl_bias_table_scaled_f32": (c_int, [c_vp, c_int, c_vp, c_vp, c_vp, c_int, c_int, c_f32, c_vp, c_vp]),
+    "grl_tc_pack_bf16": (c_int, [c_vp, c_i64, c_vp, c_i64, c_int, c_int, c_vp]),
+    "grl_tc_unpack_bf16": (c_int, [c_vp, c_i64, c_int, c_vp, c_i64, c_i64, c_int, c_vp]),
+    "grl_tc_avgpool_bf16": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp]),
+    "grl_tc_slot_scale": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_vp]),
+    "grl_tc_channel_gate_workspace": (c_sz, [c_int, c_i64, c_int]),
+    "grl_tc_channel_gate": (c_int, [c_vp, c_i64, c_int, c_i64, c_int, c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_vp, c_sz, c_vp]),
+    "grl_tc_gemm": (c_int, [ctypes.POINTER(GrlTcGemm), c_vp]),
+    "grl_tc_attn": (c_int, [ctypes.POINTER(GrlTcAttn), c_vp]),
     "grl_affine_f32": (c_int, [c_vp, c_i64, c_int, c_int, c_int, c_vp, c_vp, c_int, c_vp, c_vp, c_int, c_vp]),
     "grl_linear_f32": (c_int, [c_vp, c_i64, c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_i64, c_int, c_int, c_int, c_f32, c_vp]),
     "grl_conv3x3_f32": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_f32, c_vp]),

@@ -4,6 +4,7 @@
 
 #include "grl_common.cuh"
 #include "ops_f32.h"
+#include "ops_tc.h"
 
 namespace grl {
 char* error_buffer() {
@@ -98,7 +99,12 @@ int grl_coords_table_host(int wh, int ww, int df, float* out) {
 // ---------------------------------------------------------------- fp32 operators
 int grl_bias_table_f32(const float* table, int rows, const float* w1, const float* b1, const float* w2, int hidden,
                        int heads, float* out, void* stream) {
-  return launch_bias_table(table, rows, w1, b1, w2, hidden, heads, out, (cudaStream_t)stream);
+  return launch_bias_table(table, rows, w1, b1, w2, hidden, heads, 1.0f, out, (cudaStream_t)stream);
+}
+
+int grl_bias_table_scaled_f32(const float* table, int rows, const float* w1, const float* b1, const float* w2,
+                              int hidden, int heads, float mul, float* out, void* stream) {
+  return launch_bias_table(table, rows, w1, b1, w2, hidden, heads, mul, out, (cudaStream_t)stream);
 }
 
 int grl_affine_f32(float* attn, int64_t B_, int heads, int n1, int n2, const float* logit_scale, const float* bias,
@@ -194,6 +200,77 @@ int grl_stripe_attn_f32(const float* qkv, int64_t ld_qkv, const float* anchor, i
   a.B = B, a.heads = heads, a.d = d;
   a.logit_scale = logit_scale2, a.bias = bias2, a.rows = rows, a.use_mask = use_mask;
   return launch_attn(a, (cudaStream_t)stream);
+}
+
+// ---------------------------------------------------------------- bf16 tensor-core operators
+int grl_tc_pack_bf16(const float* x, int64_t ldx, void* y, int64_t M, int C, int Cpad, void* stream) {
+  return tc::launch_pack_bf16(x, ldx, (__nv_bfloat16*)y, M, C, Cpad, (cudaStream_t)stream);
+}
+int grl_tc_unpack_bf16(const void* x, int64_t ldx, int x_off, float* y, int64_t ldy, int64_t M, int C, void* stream) {
+  return tc::launch_unpack_bf16((const __nv_bfloat16*)x, ldx, x_off, y, ldy, M, C, (cudaStream_t)stream);
+}
+int grl_tc_avgpool_bf16(const void* x, void* y, int B, int H, int W, int Cpad, int df, void* stream) {
+  return tc::launch_avgpool_bf16((const __nv_bfloat16*)x, (__nv_bfloat16*)y, B, H, W, Cpad, df, (cudaStream_t)stream);
+}
+int grl_tc_slot_scale(const float* ls_w, const float* ls_s1, const float* ls_s2, int hw, int hs, float* out,
+                      void* stream) {
+  GRL_REQUIRE(hw >= 1 && hs >= 1 && hw <= 8 && hs <= 8, "slot_scale: bad head counts");
+  return tc::launch_slot_scale(ls_w, ls_s1, ls_s2, hw, hs, out, (cudaStream_t)stream);
+}
+size_t grl_tc_channel_gate_workspace(int B, int64_t L, int C) { return tc::channel_partial_bf16_ws(B, L, C); }
+int grl_tc_channel_gate(const void* y, int64_t ld, int B, int64_t L, int C, const float* w1, const float* b1,
+                        const float* w2, const float* b2, int R, float* gate, void* ws, size_t ws_bytes, void* stream) {
+  if (ws_bytes < tc::channel_partial_bf16_ws(B, L, C)) return fail(GRL_ERR_WORKSPACE, "tc_channel_gate: workspace too small");
+  int chunks = 0;
+  int rc = tc::launch_channel_partial_bf16((const __nv_bfloat16*)y, B, L, ld, C, (float*)ws, &chunks, (cudaStream_t)stream);
+  if (rc != GRL_OK) return rc;
+  return launch_channel_gate_from_partial((const float*)ws, chunks, B, L, C, w1, b1, w2, b2, R, gate, (cudaStream_t)stream);
+}
+
+int grl_tc_gemm(const GrlTcGemm* p, void* stream) {
+  GRL_REQUIRE(p != nullptr, "tc_gemm: null problem");
+  if (!grl_device_ok()) return fail(GRL_ERR_ARCH, "tc_gemm: tcgen05 kernels need an sm_100 device");
+  tc::GemmTcProblem q = {p->x, p->w, p->M, p->B, p->H, p->W, p->kpad, p->npad, p->taps, p->epi};
+  tc::GemmTcArgs a;
+  memset(&a, 0, sizeof(a));
+  a.N = p->n_store, a.N_f32 = p->n_real;
+  a.bias = p->bias;
+  a.out_bf16 = (__nv_bfloat16*)p->out_bf16, a.ldo_bf16 = p->ldo_bf16;
+  a.out_f32 = p->out_f32, a.ldo_f32 = p->ldo_f32;
+  a.res_f32 = p->res_f32, a.ldr = p->ldr;
+  a.act = p->act, a.slope = p->slope;
+  a.slot_scale = p->slot_scale;
+  a.C = p->C, a.gamma = p->gamma, a.beta = p->beta, a.eps = p->eps, a.res_scale = p->res_scale;
+  a.cab_y = (const __nv_bfloat16*)p->cab_y, a.ld_caby = p->ld_caby, a.cab_gate = p->cab_gate, a.L = p->L;
+  GRL_REQUIRE(p->bias != nullptr, "tc_gemm: bias is required (pass zeros)");
+  GRL_REQUIRE(p->n_store <= p->npad && p->n_real <= p->npad, "tc_gemm: n_store/n_real exceed npad");
+  if (p->epi == tc::EPI_QKV) GRL_REQUIRE(p->slot_scale && p->out_bf16 && p->ldo_bf16 >= p->npad, "tc_gemm: QKV epilogue arguments");
+  if (p->epi == tc::EPI_LN)
+    GRL_REQUIRE(p->gamma && p->beta && p->res_f32 && p->out_f32 && p->out_bf16 && p->C > 0 && p->C <= p->npad &&
+                    p->L > 0 && (p->ldo_f32 % 4) == 0 && (p->ldo_bf16 % 8) == 0,
+                "tc_gemm: LN epilogue arguments");
+  if (p->out_bf16) GRL_REQUIRE((p->ldo_bf16 % 8) == 0, "tc_gemm: bf16 output pitch must be a multiple of 8");
+  return tc::launch_gemm_tc(q, a, (cudaStream_t)stream);
+}
+
+int grl_tc_attn(const GrlTcAttn* p, void* stream) {
+  GRL_REQUIRE(p != nullptr, "tc_attn: null problem");
+  if (!grl_device_ok()) return fail(GRL_ERR_ARCH, "tc_attn: tcgen05 kernels need an sm_100 device");
+  tc::AttnTcArgs a;
+  memset(&a, 0, sizeof(a));
+  a.gq = p->gq, a.gk = p->gk;
+  a.q = (const __nv_bfloat16*)p->q, a.ldq = p->ldq, a.q_off = p->q_off;
+  a.k = (const __nv_bfloat16*)p->k, a.ldk = p->ldk, a.k_off = p->k_off;
+  a.v = (const __nv_bfloat16*)p->v, a.ldv = p->ldv, a.v_off = p->v_off, a.v_dense = p->v_dense;
+  a.out = (__nv_bfloat16*)p->out, a.ldo = p->ldo, a.o_off = p->o_off, a.o_dense = p->o_dense;
+  a.B = p->B, a.heads = p->heads, a.bias = p->bias, a.rows = p->rows, a.use_mask = p->use_mask;
+  GRL_REQUIRE((p->ldq % 8) == 0 && (p->ldk % 8) == 0 && (p->v_dense || (p->ldv % 8) == 0) &&
+                  (p->o_dense || (p->ldo % 8) == 0) && (p->q_off % 8) == 0 && (p->k_off % 8) == 0 &&
+                  (p->v_off % 8) == 0 && (p->o_off % 8) == 0,
+              "tc_attn: pitches and offsets must be multiples of 8 elements (16 bytes)");
+  GRL_REQUIRE(p->rows == (p->gq.wh + p->gk.wh - 1) * (p->gq.ww + p->gk.ww - 1), "tc_attn: bias table has %d rows, expected %d",
+              p->rows, (p->gq.wh + p->gk.wh - 1) * (p->gq.ww + p->gk.ww - 1));
+  return tc::launch_attn_tc(a, (cudaStream_t)stream);
 }
 
 }  // extern "C"

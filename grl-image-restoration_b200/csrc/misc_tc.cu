@@ -1,0 +1,137 @@
+// misc_tc.cu -- small memory-bound kernels around the tensor-core path: fp32 -> padded bf16 packing, bf16 average
+// pooling (anchors), channel means of the CAB features, per-block preparation of the attention constants.
+#include "grl_common.cuh"
+#include "ops_tc.h"
+#include "tc_common.cuh"
+
+namespace grl {
+namespace tc {
+
+// fp32 (M, C) -> bf16 (M, Cpad), zero in [C, Cpad).  Each thread converts 8 channels (one 16-byte store).
+__global__ void pack_bf16_kernel(const float* __restrict__ x, long long ldx, __nv_bfloat16* __restrict__ y, long long M,
+                                 int C, int Cpad) {
+  const int per_row = Cpad / 8;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M * per_row) return;
+  const long long m = i / per_row;
+  const int c0 = (int)(i - m * per_row) * 8;
+  float v[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) v[e] = (c0 + e < C) ? x[m * ldx + c0 + e] : 0.f;
+  *reinterpret_cast<uint4*>(y + m * Cpad + c0) =
+      make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+}
+
+// bf16 (M, ld) -> fp32 (M, C)
+__global__ void unpack_bf16_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, int x_off, float* __restrict__ y,
+                                   long long ldy, long long M, int C) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M * C) return;
+  const long long m = i / C;
+  const int c = (int)(i - m * C);
+  y[m * ldy + c] = __bfloat162float(x[m * ldx + x_off + c]);
+}
+
+// AvgPool2d(df) on bf16 channels-last data, fp32 accumulation; 8 channels per thread.
+__global__ void avgpool_bf16_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int B, int H,
+                                    int W, int Cpad, int df) {
+  const int Ho = H / df, Wo = W / df, per = Cpad / 8;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)B * Ho * Wo * per) return;
+  const int c0 = (int)(i % per) * 8;
+  long long t = i / per;
+  const int xo = (int)(t % Wo);
+  t /= Wo;
+  const int yo = (int)(t % Ho);
+  const int b = (int)(t / Ho);
+  float s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int dy = 0; dy < df; ++dy)
+    for (int dx = 0; dx < df; ++dx) {
+      const uint4 raw = *reinterpret_cast<const uint4*>(x + (((long long)b * H + yo * df + dy) * W + xo * df + dx) * Cpad + c0);
+      const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = __bfloat1622float2(p[e]);
+        s[2 * e] += f.x;
+        s[2 * e + 1] += f.y;
+      }
+    }
+  const float inv = 1.f / (float)(df * df);
+  *reinterpret_cast<uint4*>(y + i * 8) = make_uint4(pack_bf16(s[0] * inv, s[1] * inv), pack_bf16(s[2] * inv, s[3] * inv),
+                                                    pack_bf16(s[4] * inv, s[5] * inv), pack_bf16(s[6] * inv, s[7] * inv));
+}
+
+// Deterministic partial channel sums of bf16 features y (B, L, ld): partial (B, chunks, C) fp32.
+constexpr int kPoolRowsTc = 512;
+__global__ void channel_partial_bf16_kernel(const __nv_bfloat16* __restrict__ y, long long L, long long ld, int C,
+                                            float* __restrict__ partial, int chunks) {
+  const int b = blockIdx.y, ch = blockIdx.x;
+  const long long r0 = (long long)ch * kPoolRowsTc, r1 = min(L, r0 + kPoolRowsTc);
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s = 0.f;
+    for (long long r = r0; r < r1; ++r) s += __bfloat162float(y[((long long)b * L + r) * ld + c]);
+    partial[((long long)b * chunks + ch) * C + c] = s;
+  }
+}
+
+// Per-block attention constants.  slot_scale[slot] for the packed qkv layout
+//   slots: [win q h..][win k h..][win v h..][str q h..][str k h..][str v h..]
+// q^ of the window half carries exp(min(ls_w, ln100)) * log2(e); stripe k^ carries scale1 (anchors are the queries of
+// pass 1), stripe q^ carries scale2; keys / anchors that are not scaled get 1; value slots get 0 (= leave untouched).
+__global__ void slot_scale_kernel(const float* __restrict__ ls_w, const float* __restrict__ ls_s1,
+                                  const float* __restrict__ ls_s2, int hw, int hs, float* __restrict__ out) {
+  const float LOG2E = 1.4426950408889634f, LN100 = 4.605170185988092f;
+  const int n = 3 * hw + 3 * hs;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    float v;
+    if (i < hw) v = expf(fminf(ls_w[i], LN100)) * LOG2E;
+    else if (i < 2 * hw) v = 1.f;
+    else if (i < 3 * hw) v = 0.f;
+    else if (i < 3 * hw + hs) v = expf(fminf(ls_s2[i - 3 * hw], LN100)) * LOG2E;
+    else if (i < 3 * hw + 2 * hs) v = expf(fminf(ls_s1[i - 3 * hw - hs], LN100)) * LOG2E;
+    else v = 0.f;
+    out[i] = v;
+  }
+}
+
+int launch_pack_bf16(const float* x, long long ldx, __nv_bfloat16* y, long long M, int C, int Cpad, cudaStream_t st) {
+  GRL_REQUIRE(Cpad % 8 == 0 && Cpad >= C, "pack_bf16: bad padding %d for %d channels", Cpad, C);
+  if (M == 0) return GRL_OK;
+  pack_bf16_kernel<<<ceil_div(M * (Cpad / 8), 256), 256, 0, st>>>(x, ldx, y, M, C, Cpad);
+  GRL_LAUNCH_CHECK("pack_bf16_kernel");
+  return GRL_OK;
+}
+int launch_unpack_bf16(const __nv_bfloat16* x, long long ldx, int x_off, float* y, long long ldy, long long M, int C,
+                       cudaStream_t st) {
+  if (M == 0) return GRL_OK;
+  unpack_bf16_kernel<<<ceil_div(M * C, 256), 256, 0, st>>>(x, ldx, x_off, y, ldy, M, C);
+  GRL_LAUNCH_CHECK("unpack_bf16_kernel");
+  return GRL_OK;
+}
+int launch_avgpool_bf16(const __nv_bfloat16* x, __nv_bfloat16* y, int B, int H, int W, int Cpad, int df, cudaStream_t st) {
+  GRL_REQUIRE(df >= 1 && H % df == 0 && W % df == 0 && Cpad % 8 == 0, "avgpool_bf16: bad shape");
+  long long total = (long long)B * (H / df) * (W / df) * (Cpad / 8);
+  if (total == 0) return GRL_OK;
+  avgpool_bf16_kernel<<<ceil_div(total, 256), 256, 0, st>>>(x, y, B, H, W, Cpad, df);
+  GRL_LAUNCH_CHECK("avgpool_bf16_kernel");
+  return GRL_OK;
+}
+size_t channel_partial_bf16_ws(int B, long long L, int C) { return sizeof(float) * (size_t)B * ceil_div(L, kPoolRowsTc) * C; }
+int launch_channel_partial_bf16(const __nv_bfloat16* y, int B, long long L, long long ld, int C, float* partial,
+                                int* chunks_out, cudaStream_t st) {
+  const int chunks = ceil_div(L, kPoolRowsTc);
+  *chunks_out = chunks;
+  if (B == 0) return GRL_OK;
+  channel_partial_bf16_kernel<<<dim3(chunks, B), 256, 0, st>>>(y, L, ld, C, partial, chunks);
+  GRL_LAUNCH_CHECK("channel_partial_bf16_kernel");
+  return GRL_OK;
+}
+int launch_slot_scale(const float* ls_w, const float* ls_s1, const float* ls_s2, int hw, int hs, float* out,
+                      cudaStream_t st) {
+  slot_scale_kernel<<<1, 64, 0, st>>>(ls_w, ls_s1, ls_s2, hw, hs, out);
+  GRL_LAUNCH_CHECK("slot_scale_kernel");
+  return GRL_OK;
+}
+
+}  // namespace tc
+}  // namespace grl

@@ -19,7 +19,7 @@ constexpr int kMaxHeads = 8;
 
 __global__ void bias_table_kernel(const float* __restrict__ table, int rows, const float* __restrict__ w1,
                                   const float* __restrict__ b1, const float* __restrict__ w2, int hidden, int heads,
-                                  float* __restrict__ out) {
+                                  float mul, float* __restrict__ out) {
   extern __shared__ float sm[];  // w1 (hidden*2) | b1 (hidden) | w2 (heads*hidden)
   float* s_w1 = sm;
   float* s_b1 = sm + 2 * hidden;
@@ -43,7 +43,7 @@ __global__ void bias_table_kernel(const float* __restrict__ table, int rows, con
   }
 #pragma unroll
   for (int h = 0; h < kMaxHeads; ++h)
-    if (h < heads) out[(size_t)h * rows + r] = 16.f / (1.f + expf(-acc[h]));
+    if (h < heads) out[(size_t)h * rows + r] = (16.f / (1.f + expf(-acc[h]))) * mul;
 }
 
 // =====================================================================================
@@ -398,12 +398,12 @@ __global__ void __launch_bounds__(kQT) attn_f32_kernel(AttnArgs a) {
 // host launchers
 // -------------------------------------------------------------------------------------
 int launch_bias_table(const float* table, int rows, const float* w1, const float* b1, const float* w2, int hidden,
-                      int heads, float* out, cudaStream_t st) {
+                      int heads, float mul, float* out, cudaStream_t st) {
   GRL_REQUIRE(heads >= 1 && heads <= kMaxHeads, "bias_table: heads=%d unsupported (max %d)", heads, kMaxHeads);
   GRL_REQUIRE(rows > 0 && hidden > 0, "bias_table: empty");
   size_t smem = sizeof(float) * (size_t)(3 + heads) * hidden;
   GRL_REQUIRE(smem <= 48 * 1024, "bias_table: hidden=%d too large", hidden);
-  bias_table_kernel<<<ceil_div(rows, 128), 128, smem, st>>>(table, rows, w1, b1, w2, hidden, heads, out);
+  bias_table_kernel<<<ceil_div(rows, 128), 128, smem, st>>>(table, rows, w1, b1, w2, hidden, heads, mul, out);
   GRL_LAUNCH_CHECK("bias_table_kernel");
   return GRL_OK;
 }
@@ -466,6 +466,15 @@ int launch_channel_gate(const float* y, int B, long long L, int C, const float* 
   channel_partial_kernel<<<dim3(chunks, B), 256, 0, st>>>(y, L, C, (float*)ws, chunks);
   GRL_LAUNCH_CHECK("channel_partial_kernel");
   channel_gate_kernel<<<B, 256, sizeof(float) * (C + R), st>>>((const float*)ws, chunks, L, C, w1, b1, w2, b2, R, gate);
+  GRL_LAUNCH_CHECK("channel_gate_kernel");
+  return GRL_OK;
+}
+
+int launch_channel_gate_from_partial(const float* partial, int chunks, int B, long long L, int C, const float* w1,
+                                     const float* b1, const float* w2, const float* b2, int R, float* gate,
+                                     cudaStream_t st) {
+  if (B == 0) return GRL_OK;
+  channel_gate_kernel<<<B, 256, sizeof(float) * (C + R), st>>>(partial, chunks, L, C, w1, b1, w2, b2, R, gate);
   GRL_LAUNCH_CHECK("channel_gate_kernel");
   return GRL_OK;
 }

@@ -46,7 +46,7 @@ struct AttnArgs {
 };
 
 int launch_bias_table(const float* table, int rows, const float* w1, const float* b1, const float* w2, int hidden,
-                      int heads, float* out, cudaStream_t st);
+                      int heads, float mul, float* out, cudaStream_t st);
 int launch_affine(float* attn, long long B_, int heads, int n1, int n2, const float* logit_scale, const float* bias,
                   int rows, const long long* index, const float* mask, int nW, cudaStream_t st);
 int launch_gemm(const GemmArgs& a, bool conv, cudaStream_t st);
@@ -57,6 +57,9 @@ int launch_ln_residual(const float* x, const float* u, const float* gamma, const
 size_t channel_gate_ws(int B, long long L, int C);
 int launch_channel_gate(const float* y, int B, long long L, int C, const float* w1, const float* b1, const float* w2,
                         const float* b2, int R, float* gate, void* ws, size_t ws_bytes, cudaStream_t st);
+int launch_channel_gate_from_partial(const float* partial, int chunks, int B, long long L, int C, const float* w1,
+                                     const float* b1, const float* w2, const float* b2, int R, float* gate,
+                                     cudaStream_t st);
 int check_grid(const GrlGrid& g, const char* what);
 int launch_attn(const AttnArgs& a, cudaStream_t st);
 

@@ -1,0 +1,93 @@
+// ops_tc.h -- launcher declarations of the bf16 tensor-core path (gemm_tc.cu, attn_tc.cu, misc_tc.cu).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/grl_b200.h"
+
+namespace grl {
+namespace tc {
+
+enum { EPI_BIAS_ACT = 0, EPI_QKV = 1, EPI_LN = 2 };
+
+struct GemmTcArgs {
+  // filled by launch_gemm_tc
+  long long M;
+  int nk, taps;
+  int H, W, tiles_x, tiles_y;
+  // epilogue
+  int N;      // columns computed/stored as bf16 (zero beyond the real outputs)
+  int N_f32;  // real outputs (fp32 store / residual width)
+  const float* bias;  // (npad), zero in the pad
+  __nv_bfloat16* out_bf16;
+  long long ldo_bf16;
+  float* out_f32;
+  long long ldo_f32;
+  const float* res_f32;
+  long long ldr;
+  int act;
+  float slope;
+  // EPI_QKV
+  const float* slot_scale;  // per 32-wide slot: > 0 normalise and multiply, <= 0 leave as is
+  // EPI_LN
+  int C;
+  const float* gamma;
+  const float* beta;
+  float eps, res_scale;
+  const __nv_bfloat16* cab_y;
+  long long ld_caby;
+  const float* cab_gate;
+  long long L;
+};
+
+struct GemmTcProblem {
+  const void* x;  // bf16 activations
+  const void* w;  // bf16 weights (npad, taps*kpad)
+  long long M;    // linear: rows
+  int B, H, W;    // conv: image
+  int kpad, npad, taps, epi;
+};
+
+int launch_gemm_tc(const GemmTcProblem& p, GemmTcArgs a, cudaStream_t st);
+
+// Fused attention on packed bf16 head slots (32 wide).  See attn_tc.cu.
+struct AttnTcArgs {
+  GrlGrid gq, gk;
+  const __nv_bfloat16* q;
+  long long ldq;  // elements per token row
+  int q_off;      // element offset of head 0's slot
+  const __nv_bfloat16* k;
+  long long ldk;
+  int k_off;
+  const __nv_bfloat16* v;
+  long long ldv;
+  int v_off;
+  int v_dense;  // V is the dense (B_, heads, Nk, 32) X1 buffer
+  __nv_bfloat16* out;
+  long long ldo;
+  int o_off;
+  int o_dense;
+  int B, heads;
+  const float* bias;  // (heads, rows) fp32, log2 domain
+  int rows;
+  int use_mask;
+};
+int launch_attn_tc(const AttnTcArgs& a, cudaStream_t st);
+
+}  // namespace tc
+}  // namespace grl
+
+namespace grl {
+namespace tc {
+int launch_pack_bf16(const float* x, long long ldx, __nv_bfloat16* y, long long M, int C, int Cpad, cudaStream_t st);
+int launch_unpack_bf16(const __nv_bfloat16* x, long long ldx, int x_off, float* y, long long ldy, long long M, int C,
+                       cudaStream_t st);
+int launch_avgpool_bf16(const __nv_bfloat16* x, __nv_bfloat16* y, int B, int H, int W, int Cpad, int df, cudaStream_t st);
+size_t channel_partial_bf16_ws(int B, long long L, int C);
+int launch_channel_partial_bf16(const __nv_bfloat16* y, int B, long long L, long long ld, int C, float* partial,
+                                int* chunks_out, cudaStream_t st);
+int launch_slot_scale(const float* ls_w, const float* ls_s1, const float* ls_s2, int hw, int hs, float* out,
+                      cudaStream_t st);
+}  // namespace tc
+}  // namespace grl

@@ -1,0 +1,311 @@
+"""bf16 tensor-core execution of a GRL block / stage / network (the throughput path).
+
+Host-side orchestration only: one-time weight packing (pad head_dim to 32-wide slots, pad channel pitches to
+multiples of 64, permute the QKV rows into [window q|k|v][stripe q|k|v] x head order, im2col-order the 3x3 kernels)
+and the launch sequence of the tcgen05 kernels behind the C ABI (grl_tc_gemm / grl_tc_attn, include/grl_b200.h).
+Numerics contract: bf16 only for MMA operands; residual stream, LayerNorm, L2-normalisation, softmax
+statistics and every accumulator are fp32.
+Reference semantics: mixed_attn_block_efficient.py:351-381,:539-556; mixed_attn_block.py:948-983; grl.py:164-170,:506-551.
+"""
+import ctypes
+import math
+
+import torch
+
+from . import capi
+from . import functional as K
+from . import geometry as G
+
+LOG2E = 1.4426950408889634
+EPI_BIAS_ACT, EPI_QKV, EPI_LN = 0, 1, 2
+SLOT = 32
+
+
+def round_up(a, b):
+    return (a + b - 1) // b * b
+
+
+def supported(C, heads_w, heads_s):
+    c = C // 2
+    return (C % 4 == 0 and c % heads_w == 0 and c % heads_s == 0 and c // heads_w <= SLOT and c // heads_s <= SLOT
+            and heads_w <= 8 and heads_s <= 8)
+
+
+def _bf16(*shape, device, zero=False):
+    return (torch.zeros if zero else torch.empty)(*shape, device=device, dtype=torch.bfloat16)
+
+
+def pack_rows(x, cpad):
+    """fp32 (..., C) contiguous -> bf16 (..., cpad), zero padded."""
+    C = x.shape[-1]
+    M = x.numel() // C
+    y = _bf16(*x.shape[:-1], cpad, device=x.device)
+    capi.check(capi.lib().grl_tc_pack_bf16(capi.ptr(x), C, capi.ptr(y), M, C, cpad, capi.stream()))
+    return y
+
+
+def unpack_rows(x16, C, off=0):
+    """bf16 (..., ld) -> fp32 (..., C) taking columns [off, off + C)."""
+    ld = x16.shape[-1]
+    M = x16.numel() // ld
+    y = torch.empty(*x16.shape[:-1], C, device=x16.device, dtype=torch.float32)
+    capi.check(capi.lib().grl_tc_unpack_bf16(capi.ptr(x16), ld, off, capi.ptr(y), C, M, C, capi.stream()))
+    return y
+
+
+def _pad_matrix(w, npad, kpad, row_map=None, col_map=None):
+    """Scatter fp32 (N, K) into bf16 (npad, kpad): dest row row_map[i] <- src row i, dest col col_map[j] <- src col j."""
+    N, Kd = w.shape
+    out = torch.zeros(npad, kpad, device=w.device, dtype=torch.float32)
+    r = torch.arange(N, device=w.device) if row_map is None else torch.as_tensor(row_map, device=w.device)
+    c = torch.arange(Kd, device=w.device) if col_map is None else torch.as_tensor(col_map, device=w.device)
+    out[r[:, None], c[None, :]] = w.detach().float()
+    return out.to(torch.bfloat16).contiguous()
+
+
+def _pad_vector(b, npad, row_map=None):
+    out = torch.zeros(npad, device=b.device, dtype=torch.float32)
+    if b is not None:
+        r = torch.arange(b.numel(), device=b.device) if row_map is None else torch.as_tensor(row_map, device=b.device)
+        out[r] = b.detach().float()
+    return out
+
+
+def pack_conv(conv, cin_pad, npad):
+    """nn.Conv2d(3x3) weight (Cout, Cin, 3, 3) -> bf16 (npad, 9*cin_pad), k = (ky*3+kx)*cin_pad + c; bias fp32 (npad)."""
+    w = conv.weight.detach().float()
+    co, ci = w.shape[:2]
+    out = torch.zeros(npad, 9, cin_pad, device=w.device, dtype=torch.float32)
+    out[:co, :, :ci] = w.permute(0, 2, 3, 1).reshape(co, 9, ci)
+    bias = torch.zeros(npad, device=w.device, dtype=torch.float32)
+    if conv.bias is not None:
+        bias[:co] = conv.bias.detach().float()
+    return out.reshape(npad, 9 * cin_pad).to(torch.bfloat16).contiguous(), bias
+
+
+def gemm(x16, w16, bias, *, M=0, image=None, kpad, npad, taps=1, epi=EPI_BIAS_ACT, n_store=0, n_real=0, out_bf16=None,
+         out_f32=None, res_f32=None, act=K.ACT_NONE, slope=0.0, slot_scale=None, C=0, gamma=None, beta=None, eps=1e-5,
+         res_scale=1.0, cab_y=None, cab_gate=None, L=1):
+    p = capi.GrlTcGemm()
+    p.x, p.w, p.bias = x16.data_ptr(), w16.data_ptr(), bias.data_ptr()
+    p.M = M
+    if image is not None:
+        p.B, p.H, p.W = image
+    p.kpad, p.npad, p.taps, p.epi = kpad, npad, taps, epi
+    p.n_store, p.n_real = n_store, n_real
+    if out_bf16 is not None:
+        p.out_bf16, p.ldo_bf16 = out_bf16.data_ptr(), out_bf16.shape[-1]
+    if out_f32 is not None:
+        p.out_f32, p.ldo_f32 = out_f32.data_ptr(), out_f32.shape[-1]
+    if res_f32 is not None:
+        p.res_f32, p.ldr = res_f32.data_ptr(), res_f32.shape[-1]
+    p.act, p.slope = act, slope
+    if slot_scale is not None:
+        p.slot_scale = slot_scale.data_ptr()
+    p.C = C
+    if gamma is not None:
+        p.gamma, p.beta = gamma.data_ptr(), beta.data_ptr()
+    p.eps, p.res_scale = eps, res_scale
+    if cab_y is not None:
+        p.cab_y, p.ld_caby, p.cab_gate = cab_y.data_ptr(), cab_y.shape[-1], cab_gate.data_ptr()
+    p.L = L
+    capi.check(capi.lib().grl_tc_gemm(ctypes.byref(p), capi.stream()))
+
+
+def attention(gq, gk, q, q_off, k, k_off, v, v_off, out, o_off, B, heads, bias, use_mask, v_dense=False,
+              o_dense=False, tag="attn"):
+    p = capi.GrlTcAttn()
+    p.gq, p.gk = gq, gk
+    p.q, p.ldq, p.q_off = q.data_ptr(), q.shape[-1], q_off
+    p.k, p.ldk, p.k_off = k.data_ptr(), k.shape[-1], k_off
+    p.v, p.ldv, p.v_off, p.v_dense = v.data_ptr(), v.shape[-1], v_off, int(v_dense)
+    p.out, p.ldo, p.o_off, p.o_dense = out.data_ptr(), out.shape[-1], o_off, int(o_dense)
+    p.B, p.heads, p.bias, p.rows, p.use_mask = B, heads, bias.data_ptr(), bias.shape[1], int(use_mask)
+    K._timed(tag, lambda: capi.check(capi.lib().grl_tc_attn(ctypes.byref(p), capi.stream())))
+
+
+def bias_table_log2(transform, table):
+    t = table.reshape(-1, 2)
+    w1, b1, w2 = transform.cpb_mlp[0].weight, transform.cpb_mlp[0].bias, transform.cpb_mlp[2].weight
+    heads, hidden = w2.shape
+    out = torch.empty(heads, t.shape[0], device=t.device, dtype=torch.float32)
+    capi.check(capi.lib().grl_bias_table_scaled_f32(capi.ptr(t), t.shape[0], capi.ptr(w1), capi.ptr(b1), capi.ptr(w2),
+                                                    hidden, heads, LOG2E, capi.ptr(out), capi.stream()))
+    return out
+
+
+def conv3x3(x16, wpack, bias, cin_pad, npad, *, n_store, n_real=0, act=K.ACT_NONE, slope=0.0, out_bf16=None,
+            out_f32=None, res_f32=None):
+    """x16 bf16 (B, H, W, cin_pad) channels-last."""
+    B, H, W, _ = x16.shape
+    gemm(x16, wpack, bias, image=(B, H, W), kpad=cin_pad, npad=npad, taps=9, epi=EPI_BIAS_ACT, n_store=n_store,
+         n_real=n_real, out_bf16=out_bf16, out_f32=out_f32, res_f32=res_f32, act=act, slope=slope)
+
+
+def _version_key(module):
+    return tuple((p.data_ptr(), p._version) for p in module.parameters())
+
+
+class BlockPlan:
+    """Packed weights + launch sequence of one EfficientMixAttnTransformerBlock."""
+
+    def __init__(self, blk):
+        self.key = _version_key(blk)
+        at = blk.attn
+        C = blk.dim
+        c = C // 2
+        hw, hs = at.window_attn.num_heads, at.stripe_attn.num_heads
+        dw, ds = c // hw, c // hs
+        self.C, self.cpad, self.hw, self.hs = C, round_up(C, 64), hw, hs
+        self.nslots = 3 * hw + 3 * hs
+        # --- QKV: dest row = slot*32 + e
+        rmap = []
+        for half, (h, d) in enumerate(((hw, dw), (hs, ds))):
+            slot_base = 0 if half == 0 else 3 * hw
+            for t in range(3):
+                for head in range(h):
+                    for e in range(d):
+                        rmap.append((slot_base + t * h + head) * SLOT + e)
+        # source rows are already ordered (half, t, head, e) in the reference layout (efficient.py:150,:251,:362)
+        self.n_qkv = self.nslots * SLOT
+        self.w_qkv = _pad_matrix(at.qkv.body.weight, self.n_qkv, self.cpad, row_map=rmap)
+        self.b_qkv = _pad_vector(at.qkv.body.bias if at.qkv.body.bias is not None else torch.zeros(3 * C, device=at.qkv.body.weight.device), self.n_qkv, rmap)
+        # --- anchor projection: dest row = head*32 + e
+        amap = [head * SLOT + e for head in range(hs) for e in range(ds)]
+        red = at.anchor.body[0].reduction
+        self.n_anc = hs * SLOT
+        self.w_anc = _pad_matrix(red.weight, round_up(self.n_anc, 32), self.cpad, row_map=amap)
+        self.b_anc = _pad_vector(red.bias, round_up(self.n_anc, 32), amap)
+        self.anc_scale = torch.ones(hs, device=red.weight.device, dtype=torch.float32)
+        self.df = at.anchor.body[0].down_factor
+        # --- output projection: K index = slot*32 + e over [window heads | stripe heads]
+        cmap = [head * SLOT + e for head in range(hw) for e in range(dw)] + \
+               [(hw + head) * SLOT + e for head in range(hs) for e in range(ds)]
+        self.k_proj = round_up((hw + hs) * SLOT, 64)
+        self.n_ln = 64 if C <= 64 else 128 if C <= 128 else 192 if C <= 192 else 256
+        self.w_proj = _pad_matrix(at.proj.weight, self.n_ln, self.k_proj, col_map=cmap)
+        self.b_proj = _pad_vector(at.proj.bias, self.n_ln)
+        # --- MLP
+        hid = blk.mlp.fc1.weight.shape[0]
+        self.hid, self.hpad = hid, round_up(hid, 64)
+        self.w_fc1 = _pad_matrix(blk.mlp.fc1.weight, self.hpad, self.cpad)
+        self.b_fc1 = _pad_vector(blk.mlp.fc1.bias, self.hpad)
+        self.w_fc2 = _pad_matrix(blk.mlp.fc2.weight, self.n_ln, self.hpad)
+        self.b_fc2 = _pad_vector(blk.mlp.fc2.bias, self.n_ln)
+        # --- CAB
+        self.cab = bool(blk.args.local_connection)
+        if self.cab:
+            c0, c2 = blk.conv.cab[0], blk.conv.cab[2]
+            self.cmid = c0.weight.shape[0]
+            self.cmid_pad = round_up(self.cmid, 64)
+            self.w_cab1, self.b_cab1 = pack_conv(c0, self.cpad, self.cmid_pad)
+            self.w_cab2, self.b_cab2 = pack_conv(c2, self.cmid_pad, self.cpad)
+            a1, a3 = blk.conv.cab[3].attention[1], blk.conv.cab[3].attention[3]
+            self.ca = (a1.weight.detach().reshape(a1.weight.shape[0], -1).contiguous(), a1.bias.detach(),
+                       a3.weight.detach().reshape(a3.weight.shape[0], -1).contiguous(), a3.bias.detach())
+
+    @torch.no_grad()
+    def run(self, blk, x32, x16, x_size, t):
+        """x32 fp32 (B, L, C), x16 bf16 (B, L, cpad) or None -> (x32', x16')."""
+        B, L, C = x32.shape
+        H, W = x_size
+        dev = x32.device
+        at = blk.attn
+        hw, hs, cpad = self.hw, self.hs, self.cpad
+        if x16 is None:
+            x16 = pack_rows(x32, cpad)
+        lib = capi.lib()
+        # attention constants of this block
+        slot_scale = torch.empty(self.nslots, device=dev, dtype=torch.float32)
+        wa, sa = at.window_attn, at.stripe_attn
+        capi.check(lib.grl_tc_slot_scale(capi.ptr(wa.attn_transform.logit_scale), capi.ptr(sa.attn_transform1.logit_scale),
+                                         capi.ptr(sa.attn_transform2.logit_scale), hw, hs, capi.ptr(slot_scale),
+                                         capi.stream()))
+        bias_w = bias_table_log2(wa.attn_transform, t["table_w"])
+        bias_1 = bias_table_log2(sa.attn_transform1, t["table_s"])
+        bias_2 = bias_table_log2(sa.attn_transform2, t["table_s"])
+        # projections
+        qkv = _bf16(B * L, self.n_qkv, device=dev)
+        gemm(x16, self.w_qkv, self.b_qkv, M=B * L, kpad=cpad, npad=self.n_qkv, epi=EPI_QKV, n_store=self.n_qkv,
+             out_bf16=qkv, slot_scale=slot_scale)
+        df = self.df
+        pooled = _bf16(B, H // df, W // df, cpad, device=dev)
+        capi.check(lib.grl_tc_avgpool_bf16(capi.ptr(x16), capi.ptr(pooled), B, H, W, cpad, df, capi.stream()))
+        La = (H // df) * (W // df)
+        n_anc = self.w_anc.shape[0]
+        anchor = _bf16(B * La, n_anc, device=dev)
+        gemm(pooled, self.w_anc, self.b_anc, M=B * La, kpad=cpad, npad=n_anc, epi=EPI_QKV, n_store=n_anc, out_bf16=anchor,
+             slot_scale=self.anc_scale)
+        # attention
+        merged = _bf16(B * L, self.k_proj, device=dev, zero=self.k_proj != (hw + hs) * SLOT)
+        s = wa.shift_size
+        gw = G.token_grid(x_size, wa.window_size, (s, s))
+        attention(gw, gw, qkv, 0, qkv, hw * SLOT, qkv, 2 * hw * SLOT, merged, 0, B, hw, bias_w, t["mask_w"] is not None,
+                  tag="window_attn")
+        tok, anc = sa.grids(x_size)
+        nW = (tok.H // tok.wh) * (tok.W // tok.ww)
+        x1 = _bf16(B * nW * hs * anc.wh * anc.ww, SLOT, device=dev)
+        use_mask = t["mask_a2w"] is not None
+        attention(anc, tok, anchor, 0, qkv, (3 * hw + hs) * SLOT, qkv, (3 * hw + 2 * hs) * SLOT, x1, 0, B, hs, bias_1,
+                  use_mask, o_dense=True, tag="stripe_attn")
+        attention(tok, anc, qkv, 3 * hw * SLOT, anchor, 0, x1, 0, merged, hw * SLOT, B, hs, bias_2, use_mask,
+                  v_dense=True, tag="stripe_attn")
+        # CAB
+        cab_y = gate = None
+        if self.cab:
+            t1 = _bf16(B, H, W, self.cmid_pad, device=dev)
+            conv3x3(x16.view(B, H, W, cpad), self.w_cab1, self.b_cab1, cpad, self.cmid_pad, n_store=self.cmid_pad,
+                    act=K.ACT_GELU, out_bf16=t1)
+            cab_y = _bf16(B * L, cpad, device=dev)
+            conv3x3(t1, self.w_cab2, self.b_cab2, self.cmid_pad, cpad, n_store=cpad, out_bf16=cab_y)
+            nbytes = lib.grl_tc_channel_gate_workspace(B, L, C)
+            ws = torch.empty(max(nbytes, 4) // 4, device=dev, dtype=torch.float32)
+            gate = torch.empty(B, C, device=dev, dtype=torch.float32)
+            w1, b1, w2, b2 = self.ca
+            capi.check(lib.grl_tc_channel_gate(capi.ptr(cab_y), cpad, B, L, C, capi.ptr(w1), capi.ptr(b1), capi.ptr(w2),
+                                               capi.ptr(b2), w1.shape[0], capi.ptr(gate), capi.ptr(ws), nbytes,
+                                               capi.stream()))
+        # proj + LN1 + residual (+ CAB)
+        y32 = torch.empty(B, L, C, device=dev, dtype=torch.float32)
+        y16 = _bf16(B, L, cpad, device=dev)
+        gemm(merged, self.w_proj, self.b_proj, M=B * L, kpad=self.k_proj, npad=self.n_ln, epi=EPI_LN, n_store=self.n_ln,
+             n_real=C, out_bf16=y16, out_f32=y32, res_f32=x32, C=C, gamma=blk.norm1.weight, beta=blk.norm1.bias,
+             eps=blk.norm1.eps, res_scale=blk.res_scale, cab_y=cab_y, cab_gate=gate, L=L)
+        # MLP + LN2 + residual
+        hid = _bf16(B * L, self.hpad, device=dev)
+        gemm(y16, self.w_fc1, self.b_fc1, M=B * L, kpad=cpad, npad=self.hpad, epi=EPI_BIAS_ACT, n_store=self.hpad,
+             act=K.ACT_GELU, out_bf16=hid)
+        z32 = torch.empty(B, L, C, device=dev, dtype=torch.float32)
+        z16 = _bf16(B, L, cpad, device=dev)
+        gemm(hid, self.w_fc2, self.b_fc2, M=B * L, kpad=self.hpad, npad=self.n_ln, epi=EPI_LN, n_store=self.n_ln, n_real=C,
+             out_bf16=z16, out_f32=z32, res_f32=y32, C=C, gamma=blk.norm2.weight, beta=blk.norm2.bias, eps=blk.norm2.eps,
+             res_scale=blk.res_scale, L=L)
+        return z32, z16
+
+
+def block_plan(blk):
+    plan = getattr(blk, "_tc_plan", None)
+    if plan is None or plan.key != _version_key(blk):
+        plan = BlockPlan(blk)
+        blk._tc_plan = plan
+    return plan
+
+
+class ConvPlan:
+    """One packed 3x3 conv (stage conv / head convs)."""
+
+    def __init__(self, conv, cin_pad):
+        self.key = _version_key(conv)
+        self.cout = conv.weight.shape[0]
+        self.cin_pad = cin_pad
+        self.npad = round_up(self.cout, 64)
+        self.w, self.b = pack_conv(conv, cin_pad, self.npad)
+
+
+def conv_plan(owner, name, conv, cin_pad):
+    cache = owner.__dict__.setdefault("_tc_convs", {})
+    plan = cache.get(name)
+    if plan is None or plan.key != _version_key(conv) or plan.cin_pad != cin_pad:
+        plan = ConvPlan(conv, cin_pad)
+        cache[name] = plan
+    return plan

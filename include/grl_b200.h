@@ -122,6 +122,93 @@ int grl_stripe_attn_f32(const float* qkv, int64_t ld_qkv, const float* anchor, i
                         const float* bias1, const float* logit_scale2, const float* bias2, int use_mask,
                         void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- bf16 tensor-core operators (throughput path: tcgen05.mma + TMEM + TMA, sm_100a only) ----------------
+ * Activations are bf16 with channel pitches padded to a multiple of 64; attention heads live in 32-wide "slots"
+ * (head_dim zero-padded to 32).  The residual stream, LayerNorm, softmax statistics and all accumulators stay fp32. */
+
+/* grl_bias_table_f32 with the table multiplied by `mul` (log2(e) for the exp2-domain softmax of grl_tc_attn). */
+int grl_bias_table_scaled_f32(const float* table, int rows, const float* w1, const float* b1, const float* w2,
+                              int hidden, int heads, float mul, float* out, void* stream);
+
+/* fp32 (M, C) rows of pitch ldx -> bf16 (M, Cpad) zero-padded; and back (bf16 rows of pitch ldx, column offset). */
+int grl_tc_pack_bf16(const float* x, int64_t ldx, void* y_bf16, int64_t M, int C, int Cpad, void* stream);
+int grl_tc_unpack_bf16(const void* x_bf16, int64_t ldx, int x_off, float* y, int64_t ldy, int64_t M, int C, void* stream);
+/* AvgPool2d(df) on bf16 channels-last data (AnchorLinear.pooling, mixed_attn_block.py:725). */
+int grl_tc_avgpool_bf16(const void* x_bf16, void* y_bf16, int B, int H, int W, int Cpad, int df, void* stream);
+/* Per-slot multipliers of the packed qkv layout [win q|k|v][stripe q|k|v] x heads: exp(min(logit_scale, ln100))*log2(e)
+ * on window q, stripe q (attn_transform2) and stripe k (attn_transform1); 1 on the other q/k slots; 0 on v slots
+ * (mixed_attn_block_efficient.py:39). out: (3*hw + 3*hs) floats. */
+int grl_tc_slot_scale(const float* ls_window, const float* ls_stripe1, const float* ls_stripe2, int heads_w, int heads_s,
+                      float* out, void* stream);
+/* ChannelAttention gate from bf16 CAB features y (B, L, ld) (mixed_attn_block.py:948-967). */
+size_t grl_tc_channel_gate_workspace(int B, int64_t L, int C);
+int grl_tc_channel_gate(const void* y_bf16, int64_t ld, int B, int64_t L, int C, const float* w1, const float* b1,
+                        const float* w2, const float* b2, int R, float* gate, void* workspace, size_t workspace_bytes,
+                        void* stream);
+
+/* Tensor-core GEMM / implicit-GEMM 3x3 conv with a fused epilogue.  x: bf16 (M, kpad) or (B, H, W, kpad) when taps == 9;
+ * w: bf16 (npad, taps*kpad) K-major (conv: k = tap*kpad + c, tap = ky*3+kx); bias: (npad) fp32, zero in the pad.
+ *   epi 0  y = act(acc + b) (+ res_f32)           -> out_bf16 (n_store cols) and/or out_f32 (n_real cols)
+ *          nn.Linear / nn.Conv2d of Mlp.fc1, CAB, TransformerStage.conv, conv_first/after_body/upsampler heads
+ *   epi 1  per 32-wide slot: (acc + b) * slot_scale / max(||.||2, 1e-12) (slot_scale <= 0: untouched) -> out_bf16
+ *          QKVProjection / AnchorLinear.reduction fused with F.normalize + logit scale (efficient.py:39,:85)
+ *   epi 2  out = res_f32 + res_scale * LayerNorm(acc + b) (+ cab_y * cab_gate[token / L]) -> out_f32 + out_bf16
+ *          MixedAttention.proj + norm1 + CAB add, Mlp.fc2 + norm2 (efficient.py:543-554); needs npad <= 256. */
+typedef struct {
+  const void* x;
+  const void* w;
+  const float* bias;
+  int64_t M;
+  int32_t B, H, W;
+  int32_t kpad, npad, taps, epi;
+  int32_t n_store, n_real;
+  void* out_bf16;
+  int64_t ldo_bf16;
+  float* out_f32;
+  int64_t ldo_f32;
+  const float* res_f32;
+  int64_t ldr;
+  int32_t act;
+  float slope;
+  const float* slot_scale;
+  int32_t C;
+  const float* gamma;
+  const float* beta;
+  float eps, res_scale;
+  const void* cab_y;
+  int64_t ld_caby;
+  const float* cab_gate;
+  int64_t L;
+} GrlTcGemm;
+int grl_tc_gemm(const GrlTcGemm* p, void* stream);
+
+/* Fused cosine attention over packed bf16 head slots: out = softmax2(q k^T + bias + mask) v, one call per
+ * WindowAttention.forward and two per AnchorStripeAttention.forward (efficient.py:128-165,:215-270).
+ * q/k/v: bf16 token rows (pitch ld*, element offset *_off of head 0's slot); v_dense/o_dense: the (B_, heads, N, 32)
+ * intermediate X1 of the stripe attention; bias: (heads, rows) fp32 from grl_bias_table_scaled_f32(.., log2 e). */
+typedef struct {
+  GrlGrid gq, gk;
+  const void* q;
+  int64_t ldq;
+  int32_t q_off;
+  const void* k;
+  int64_t ldk;
+  int32_t k_off;
+  const void* v;
+  int64_t ldv;
+  int32_t v_off;
+  int32_t v_dense;
+  void* out;
+  int64_t ldo;
+  int32_t o_off;
+  int32_t o_dense;
+  int32_t B, heads;
+  const float* bias;
+  int32_t rows;
+  int32_t use_mask;
+} GrlTcAttn;
+int grl_tc_attn(const GrlTcAttn* p, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,68 @@
+"""bf16 tensor-core path, network level.  Gates (BASELINE.json / SURVEY.md 8d): |PSNR(cand, GT) - PSNR(ref, GT)| <= 0.01 dB
+with the reference's PSNR definition (tensor_round + shave + per-image mean), and PSNR(cand, ref) reported."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def build(pkg, oracle, cfg, device, seed=0, precision="bf16"):
+    m = pkg.GRL(**cfg)
+    m.load_state_dict(oracle.synth_state_dict(cfg, seed=seed), strict=False)
+    m = m.to(device).eval()
+    m.set_precision(precision)
+    return m
+
+
+def test_block_and_stage_bf16_vs_reference_taps(pkg, oracle, cases, golden_loader, device):
+    cfg = cases["micro_cab_x2"]["cfg"]
+    gold = golden_loader("model_micro_cab_x2.npz")
+    m = build(pkg, oracle, cfg, device)
+    assert m.precision == "bf16"
+    hw = (16, 32)
+    xb = gold["block_input"].to(device)
+    tim = m.get_table_index_mask(device, hw)
+    for bi in range(4):
+        y = m.layers[0].blocks[bi](xb, hw, tim).cpu()
+        ref = gold[f"block{bi}/out"]
+        err = (y - ref).abs()
+        print(f"block {bi}: bf16 max-abs {err.max().item():.3e} mean-abs {err.mean().item():.3e} (ref rms {ref.pow(2).mean().sqrt().item():.2f})")
+        assert err.max().item() <= 0.25 and err.mean().item() <= 2e-2
+    ys = m.layers[0](xb, hw, tim).cpu()
+    err = (ys - gold["stage0/out"]).abs()
+    print(f"stage: bf16 max-abs {err.max().item():.3e} mean-abs {err.mean().item():.3e}")
+    assert err.mean().item() <= 5e-2
+
+
+@pytest.mark.parametrize("variant,task,scale,size,hw", [("tiny", "sr", 2, 64, (64, 64)), ("small", "sr", 4, 64, (64, 64)),
+                                                        ("base", "sr", 4, 64, (64, 64)), ("small", "dn", 1, 128, (100, 120))])
+def test_psnr_gate_vs_oracle(pkg, oracle, device, variant, task, scale, size, hw):
+    cfg = pkg.configs.grl_config(variant, task, scale, size)
+    m = build(pkg, oracle, cfg, device, seed=3)
+    sd = oracle.synth_state_dict(cfg, seed=3)
+    x = oracle.synth_input((1, 3, *hw), seed=77, noise_sigma=50.0 if task == "dn" else 0.0)
+    with torch.no_grad():
+        ref = oracle.grl_forward(sd, cfg, x)
+    y = m(x.to(device)).cpu()
+    assert y.shape == ref.shape and torch.isfinite(y).all()
+    gt = torch.rand(ref.shape, generator=torch.Generator().manual_seed(9))
+    b = scale if scale > 1 else 0
+    d_psnr = abs(oracle.psnr(y, gt, b).mean().item() - oracle.psnr(ref, gt, b).mean().item())
+    p_cr = (-10 * torch.log10(((y - ref) ** 2).mean())).item()
+    print(f"{variant}/{task}: max-abs {(y - ref).abs().max().item():.3e}  PSNR(cand, ref) {p_cr:.1f} dB  |dPSNR vs GT| {d_psnr:.4f} dB")
+    assert d_psnr <= 0.01
+    assert p_cr >= 40.0
+
+
+def test_bf16_fp32_switch_and_batch_invariance(pkg, oracle, device):
+    cfg = pkg.configs.grl_config("base", "sr", 4, 256)
+    m = build(pkg, oracle, cfg, device, seed=1)
+    x = oracle.synth_input((2, 3, 256, 256), seed=1234).to(device)
+    y = m(x)
+    assert y.shape == (2, 3, 1024, 1024) and torch.isfinite(y).all()
+    assert (m(x[:1]) - y[:1]).abs().max().item() <= 1e-4
+    m.set_precision("fp32")
+    y32 = m(x[:1])
+    p = (-10 * torch.log10(((y[:1] - y32) ** 2).mean())).item()
+    print(f"base sr 256: PSNR(bf16, fp32 path) = {p:.1f} dB, max-abs {(y[:1] - y32).abs().max().item():.3e}")
+    assert p >= 40.0
