@@ -89,11 +89,26 @@ def cpu_leg(cfg_tuple, steps, warmup):
 
     pkg = load_package()
     variant, task, scale, tile, _ = cfg_tuple
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
     cfg = pkg.configs.grl_config(variant, task, scale, CPU_SAMPLE_TILE)
     sd = orc.synth_state_dict(cfg, seed=0)
     x = orc.synth_input((1, 3, CPU_SAMPLE_TILE, CPU_SAMPLE_TILE), seed=1234)
+    # "all the host threads it can use": ATen's intra-op pool stops scaling (and then collapses) long before 128
+    # threads on these small per-window ops, so pick the fastest of a few pool sizes on a 1-stage probe.
+    avail = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    probe_cfg = dict(cfg, depths=cfg["depths"][:1], num_heads_window=cfg["num_heads_window"][:1],
+                     num_heads_stripe=cfg["num_heads_stripe"][:1])
+    probe_sd = orc.synth_state_dict(probe_cfg, seed=0)
+    best, cores = None, avail
+    for n in sorted({min(avail, c) for c in (8, 16, 32, 64, avail)}):
+        torch.set_num_threads(n)
+        with torch.no_grad():
+            orc.grl_forward(probe_sd, probe_cfg, x)
+            t0 = time.perf_counter()
+            orc.grl_forward(probe_sd, probe_cfg, x)
+            dt = time.perf_counter() - t0
+        if best is None or dt < best:
+            best, cores = dt, n
+    torch.set_num_threads(cores)
     ts, y = [], None
     with torch.no_grad():
         for i in range(warmup + steps):
