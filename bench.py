@@ -90,14 +90,14 @@ def cpu_leg(cfg_tuple, steps, warmup):
     pkg = load_package()
     variant, task, scale, tile, _ = cfg_tuple
     cfg = pkg.configs.grl_config(variant, task, scale, CPU_SAMPLE_TILE)
-    sd = orc.synth_state_dict(cfg, seed=0)
+    sd = orc.synth_state_dict(cfg, seed=0, style="init")  # weights distributed like the reference constructor's
     x = orc.synth_input((1, 3, CPU_SAMPLE_TILE, CPU_SAMPLE_TILE), seed=1234)
     # "all the host threads it can use": ATen's intra-op pool stops scaling (and then collapses) long before 128
     # threads on these small per-window ops, so pick the fastest of a few pool sizes on a 1-stage probe.
     avail = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     probe_cfg = dict(cfg, depths=cfg["depths"][:1], num_heads_window=cfg["num_heads_window"][:1],
                      num_heads_stripe=cfg["num_heads_stripe"][:1])
-    probe_sd = orc.synth_state_dict(probe_cfg, seed=0)
+    probe_sd = orc.synth_state_dict(probe_cfg, seed=0, style="init")
     best, cores = None, avail
     for n in sorted({min(avail, c) for c in (8, 16, 32, 64, avail)}):
         torch.set_num_threads(n)
@@ -130,7 +130,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg4", choices=sorted(WORKLOADS))
     ap.add_argument("--tiles-per-gpu", type=int, default=None)
-    ap.add_argument("--precision", default="auto", choices=["auto", "fp32", "bf16"])
+    ap.add_argument("--precision", default="auto", choices=["auto", "fp32", "fp16", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -178,7 +178,7 @@ def main():
 
     cfg = pkg.configs.grl_config(variant, task, scale, tile)
     model = pkg.GRL(**cfg)
-    model.load_state_dict(orc.synth_state_dict(cfg, seed=0), strict=False)
+    model.load_state_dict(orc.synth_state_dict(cfg, seed=0, style="init"), strict=False)
     model = model.to(dev).eval()
     precision = a.precision
     if hasattr(model, "set_precision"):
@@ -269,7 +269,10 @@ def main():
 
     out = {"metric": metric, "value": value, "unit": "Mpix/s", "n_gpus": world, "steps": a.steps, "warmup": max(W, 3),
            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-           "dtype": "f32" if precision == "fp32" else "bf16", "data": "synthetic", "config": cfg_desc,
+           "dtype": {"fp32": "f32", "fp16": "f16", "bf16": "bf16"}[precision],
+           "dtype_note": "MMA operand format (tcgen05 kind::f16, fp32 accumulate); residual stream, LayerNorm, softmax "
+                         "statistics in fp32. f16 (11-bit mantissa) >= bf16 precision; --precision bf16 runs at the same speed",
+           "data": "synthetic", "config": cfg_desc,
            "output_mpix_per_s": value * scale * scale, "clocks": clocks, "gpu_launches": int(launches),
            "e2e": {"value": e2e_value, "unit": "Mpix/s", "h2d_bytes_per_step": int(x_host.numel() * 4 + gt_host.numel() * 4),
                    "d2h_bytes_per_step": int(pv.numel() * 4 + pi.numel() * 8),

@@ -144,8 +144,9 @@ __global__ void __launch_bounds__(kQT, 3) attn_tc_kernel(const AttnTcArgs a) {
   for (int e = 0; e < kDP; ++e) o[e] = 0.f;
   float m_run = -INFINITY, l_run = 0.f;
 
-  constexpr uint32_t idesc_qk = umma_idesc(kQT, KT, 1, 0, 0);
-  constexpr uint32_t idesc_pv = umma_idesc(kQT, kDP, 1, 0, 1);
+  const uint32_t idesc_qk = umma_idesc(kQT, KT, a.fmt, 0, 0);
+  const uint32_t idesc_pv = umma_idesc(kQT, kDP, a.fmt, 0, 1);
+  const int fmt = a.fmt;
   const uint32_t q_sa = smem_u32(Qs), p_sa = smem_u32(Ps);
 
   for (int t = 0; t < ntiles; ++t) {
@@ -214,7 +215,7 @@ __global__ void __launch_bounds__(kQT, 3) attn_tc_kernel(const AttnTcArgs a) {
         p[e] = ex2(lg[c * 8 + e] - m_new);
         psum += p[e];
       }
-      const uint4 pk = make_uint4(pack_bf16(p[0], p[1]), pack_bf16(p[2], p[3]), pack_bf16(p[4], p[5]), pack_bf16(p[6], p[7]));
+      const uint4 pk = make_uint4(pack16(p[0], p[1], fmt), pack16(p[2], p[3], fmt), pack16(p[4], p[5], fmt), pack16(p[6], p[7], fmt));
       // [128 x KT] K-major SWIZZLE_128B, 64-key sub-tiles of 16 KB
       const int sub = c >> 3, cc = c & 7;
       *reinterpret_cast<uint4*>(Ps + sub * (kQT * 128) + tid * 128 + ((cc ^ (tid & 7)) << 4)) = pk;
@@ -257,8 +258,8 @@ __global__ void __launch_bounds__(kQT, 3) attn_tc_kernel(const AttnTcArgs a) {
 #pragma unroll
     for (int e = 0; e < kDP; e += 8)
       *reinterpret_cast<uint4*>(dst + e) =
-          make_uint4(pack_bf16(o[e] * inv, o[e + 1] * inv), pack_bf16(o[e + 2] * inv, o[e + 3] * inv),
-                     pack_bf16(o[e + 4] * inv, o[e + 5] * inv), pack_bf16(o[e + 6] * inv, o[e + 7] * inv));
+          make_uint4(pack16(o[e] * inv, o[e + 1] * inv, fmt), pack16(o[e + 2] * inv, o[e + 3] * inv, fmt),
+                     pack16(o[e + 4] * inv, o[e + 5] * inv, fmt), pack16(o[e + 6] * inv, o[e + 7] * inv, fmt));
   }
   __syncthreads();
   if (warp == 0) {

@@ -203,14 +203,22 @@ int grl_stripe_attn_f32(const float* qkv, int64_t ld_qkv, const float* anchor, i
 }
 
 // ---------------------------------------------------------------- bf16 tensor-core operators
-int grl_tc_pack_bf16(const float* x, int64_t ldx, void* y, int64_t M, int C, int Cpad, void* stream) {
-  return tc::launch_pack_bf16(x, ldx, (__nv_bfloat16*)y, M, C, Cpad, (cudaStream_t)stream);
+static int check_fmt(int fmt) {
+  GRL_REQUIRE(fmt == 0 || fmt == 1, "tc: operand format must be 0 (fp16) or 1 (bf16), got %d", fmt);
+  return GRL_OK;
 }
-int grl_tc_unpack_bf16(const void* x, int64_t ldx, int x_off, float* y, int64_t ldy, int64_t M, int C, void* stream) {
-  return tc::launch_unpack_bf16((const __nv_bfloat16*)x, ldx, x_off, y, ldy, M, C, (cudaStream_t)stream);
+int grl_tc_pack16(const float* x, int64_t ldx, void* y, int64_t M, int C, int Cpad, int fmt, void* stream) {
+  if (check_fmt(fmt)) return GRL_ERR_INVALID;
+  return tc::launch_pack_bf16(x, ldx, y, M, C, Cpad, fmt, (cudaStream_t)stream);
 }
-int grl_tc_avgpool_bf16(const void* x, void* y, int B, int H, int W, int Cpad, int df, void* stream) {
-  return tc::launch_avgpool_bf16((const __nv_bfloat16*)x, (__nv_bfloat16*)y, B, H, W, Cpad, df, (cudaStream_t)stream);
+int grl_tc_unpack16(const void* x, int64_t ldx, int x_off, float* y, int64_t ldy, int64_t M, int C, int fmt,
+                    void* stream) {
+  if (check_fmt(fmt)) return GRL_ERR_INVALID;
+  return tc::launch_unpack_bf16(x, ldx, x_off, y, ldy, M, C, fmt, (cudaStream_t)stream);
+}
+int grl_tc_avgpool16(const void* x, void* y, int B, int H, int W, int Cpad, int df, int fmt, void* stream) {
+  if (check_fmt(fmt)) return GRL_ERR_INVALID;
+  return tc::launch_avgpool_bf16(x, y, B, H, W, Cpad, df, fmt, (cudaStream_t)stream);
 }
 int grl_tc_slot_scale(const float* ls_w, const float* ls_s1, const float* ls_s2, int hw, int hs, float* out,
                       void* stream) {
@@ -218,11 +226,12 @@ int grl_tc_slot_scale(const float* ls_w, const float* ls_s1, const float* ls_s2,
   return tc::launch_slot_scale(ls_w, ls_s1, ls_s2, hw, hs, out, (cudaStream_t)stream);
 }
 size_t grl_tc_channel_gate_workspace(int B, int64_t L, int C) { return tc::channel_partial_bf16_ws(B, L, C); }
-int grl_tc_channel_gate(const void* y, int64_t ld, int B, int64_t L, int C, const float* w1, const float* b1,
+int grl_tc_channel_gate(const void* y, int64_t ld, int fmt, int B, int64_t L, int C, const float* w1, const float* b1,
                         const float* w2, const float* b2, int R, float* gate, void* ws, size_t ws_bytes, void* stream) {
+  if (check_fmt(fmt)) return GRL_ERR_INVALID;
   if (ws_bytes < tc::channel_partial_bf16_ws(B, L, C)) return fail(GRL_ERR_WORKSPACE, "tc_channel_gate: workspace too small");
   int chunks = 0;
-  int rc = tc::launch_channel_partial_bf16((const __nv_bfloat16*)y, B, L, ld, C, (float*)ws, &chunks, (cudaStream_t)stream);
+  int rc = tc::launch_channel_partial_bf16(y, B, L, ld, C, fmt, (float*)ws, &chunks, (cudaStream_t)stream);
   if (rc != GRL_OK) return rc;
   return launch_channel_gate_from_partial((const float*)ws, chunks, B, L, C, w1, b1, w2, b2, R, gate, (cudaStream_t)stream);
 }
@@ -233,15 +242,17 @@ int grl_tc_gemm(const GrlTcGemm* p, void* stream) {
   tc::GemmTcProblem q = {p->x, p->w, p->M, p->B, p->H, p->W, p->kpad, p->npad, p->taps, p->epi};
   tc::GemmTcArgs a;
   memset(&a, 0, sizeof(a));
+  if (check_fmt(p->fmt)) return GRL_ERR_INVALID;
+  a.fmt = p->fmt;
   a.N = p->n_store, a.N_f32 = p->n_real;
   a.bias = p->bias;
-  a.out_bf16 = (__nv_bfloat16*)p->out_bf16, a.ldo_bf16 = p->ldo_bf16;
+  a.out_bf16 = p->out_bf16, a.ldo_bf16 = p->ldo_bf16;
   a.out_f32 = p->out_f32, a.ldo_f32 = p->ldo_f32;
   a.res_f32 = p->res_f32, a.ldr = p->ldr;
   a.act = p->act, a.slope = p->slope;
   a.slot_scale = p->slot_scale;
   a.C = p->C, a.gamma = p->gamma, a.beta = p->beta, a.eps = p->eps, a.res_scale = p->res_scale;
-  a.cab_y = (const __nv_bfloat16*)p->cab_y, a.ld_caby = p->ld_caby, a.cab_gate = p->cab_gate, a.L = p->L;
+  a.cab_y = p->cab_y, a.ld_caby = p->ld_caby, a.cab_gate = p->cab_gate, a.L = p->L;
   GRL_REQUIRE(p->bias != nullptr, "tc_gemm: bias is required (pass zeros)");
   GRL_REQUIRE(p->n_store <= p->npad && p->n_real <= p->npad, "tc_gemm: n_store/n_real exceed npad");
   if (p->epi == tc::EPI_QKV) GRL_REQUIRE(p->slot_scale && p->out_bf16 && p->ldo_bf16 >= p->npad, "tc_gemm: QKV epilogue arguments");
@@ -258,6 +269,8 @@ int grl_tc_attn(const GrlTcAttn* p, void* stream) {
   if (!grl_device_ok()) return fail(GRL_ERR_ARCH, "tc_attn: tcgen05 kernels need an sm_100 device");
   tc::AttnTcArgs a;
   memset(&a, 0, sizeof(a));
+  if (check_fmt(p->fmt)) return GRL_ERR_INVALID;
+  a.fmt = p->fmt;
   a.gq = p->gq, a.gk = p->gk;
   a.q = (const __nv_bfloat16*)p->q, a.ldq = p->ldq, a.q_off = p->q_off;
   a.k = (const __nv_bfloat16*)p->k, a.ldk = p->ldk, a.k_off = p->k_off;

@@ -42,15 +42,31 @@ constexpr int kStages = 2;
 constexpr int kBM = 128, kBK = 64;
 constexpr int kTH = 8, kTW = 16;  // conv patch (kTH * kTW == kBM)
 
+// Epilogue staging: the accumulator tile is first written to shared memory by its row owners (phase A, thread = row,
+// straight from TMEM), then streamed to global memory row-major by all epilogue threads with 16-byte accesses
+// (phase B) -- fully coalesced residual reads and stores with many independent requests in flight.  The staging
+// tile aliases the TMA pipeline buffers (the main loop is over when the epilogue starts).
+//   fp32 staging (LayerNorm / fp32 outputs): [128][pitch32] floats, pitch32 % 8 == 4  -> conflict-free 16 B rows
+//   16-bit staging (fp16/bf16-only outputs): [128][BN + 8] halves
+__host__ __device__ constexpr int stage_pitch32(int c) { return (c % 8 == 4) ? c : ((c + 3) / 4 * 4 % 8 == 4 ? (c + 3) / 4 * 4 : (c + 3) / 4 * 4 + 4); }
+
 template <int BN>
 struct GemmSmem {
   static constexpr int A_BYTES = kBM * kBK * 2;
   static constexpr int B_BYTES = BN * kBK * 2;
   static constexpr int STAGE = A_BYTES + B_BYTES;
-  static constexpr int TOTAL = kStages * STAGE + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int PIPE = kStages * STAGE;
+  static constexpr int STG32 = kBM * stage_pitch32(BN <= 192 ? (BN == 192 ? 188 : BN) : 4) * 4;  // C <= 188 at BN = 192
+  static constexpr int STG16 = kBM * (BN + 8) * 2;
+  static constexpr int STG = (STG32 > STG16 ? STG32 : STG16);
+  static constexpr int OFF_TOK = ((PIPE > STG ? PIPE : STG) + 15) / 16 * 16;  // long long tok[128]
+  static constexpr int OFF_BAR = OFF_TOK + 128 * 8;
+  static constexpr int TOTAL = OFF_BAR + 128 + 1024 /*align slack*/;
 };
 
 __device__ __forceinline__ uint32_t tmem_cols_for(int bn) { return bn <= 32 ? 32 : bn <= 64 ? 64 : bn <= 128 ? 128 : 256; }
+
+__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
 template <int BN, int EPI, bool CONV>
 __global__ void __launch_bounds__(192, 2)
@@ -58,10 +74,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   using S = GemmSmem<BN>;
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + kStages * S::STAGE);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + S::OFF_BAR);
   uint64_t* empty = full + kStages;
   uint64_t* tmem_full = empty + kStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  long long* s_tok = reinterpret_cast<long long*>(smem + S::OFF_TOK);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = blockIdx.y * BN;
@@ -92,6 +109,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tma_prefetch_desc(&tmB);
   }
   if (warp == 1) tmem_alloc(tmem_slot, tmem_cols_for(BN));
+  if (warp >= 2) {  // token (global row) of every accumulator row, -1 = outside the problem
+    const int r = (warp & 3) * 32 + lane;
+    long long tok;
+    if (CONV) {
+      const int y = ty0 + r / kTW, x = tx0 + r % kTW;
+      tok = (y < a.H && x < a.W) ? ((long long)tb * a.H + y) * a.W + x : -1;
+    } else {
+      tok = (long long)m0 + r;
+      if (tok >= a.M) tok = -1;
+    }
+    s_tok[r] = tok;
+  }
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
@@ -117,7 +146,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc(kBM, BN, 1, 0, 0);
+      const uint32_t idesc = umma_idesc(kBM, BN, a.fmt, 0, 0);
       for (int kc = 0; kc < nk_total; ++kc) {
         const int s = kc % kStages;
         const uint32_t ph = (kc / kStages) & 1;
@@ -136,133 +165,198 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       umma_commit(tmem_full);
     }
   } else {
-    // ------------------------------------------------------------------ epilogue: one accumulator row per thread
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
-    const int r = q * 32 + lane;
-    long long tok;
-    bool row_ok;
-    if (CONV) {
-      const int y = ty0 + r / kTW, x = tx0 + r % kTW;
-      row_ok = (y < a.H) && (x < a.W);
-      tok = ((long long)tb * a.H + y) * a.W + x;
-    } else {
-      tok = (long long)m0 + r;
-      row_ok = tok < a.M;
-    }
-    mbar_wait(tmem_full, 0);
+    // ================================================================== epilogue (4 warps, 128 threads)
+    const int q = warp & 3;       // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;  // accumulator row owned in phase A
+    const int et = threadIdx.x - 64;  // 0..127
+    const int fmt = a.fmt;
+    uint16_t* out16 = reinterpret_cast<uint16_t*>(a.out_bf16);
+    mbar_wait(tmem_full, 0);  // all MMAs done -> accumulators valid AND the pipeline smem is free for staging
     tcgen05_fence_after();
     const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
     uint32_t v[32];
 
-    if (EPI == EPI_LN) {
-      // pass 1: mean, pass 2: variance (two-pass like ATen's LayerNorm), pass 3: normalise + residual
-      const int C = a.C;
-      float sum = 0.f;
-      for (int c0 = 0; c0 < C; c0 += 32) {
-        tmem_ld32(trow + c0, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (c0 + j < C) sum += __uint_as_float(v[j]) + a.bias[c0 + j];
-      }
-      const float mean = sum / (float)C;
-      float var = 0.f;
-      for (int c0 = 0; c0 < C; c0 += 32) {
-        tmem_ld32(trow + c0, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (c0 + j < C) {
-            const float d = __uint_as_float(v[j]) + a.bias[c0 + j] - mean;
-            var = fmaf(d, d, var);
-          }
-      }
-      const float rstd = rsqrtf(var / (float)C + a.eps);
-      const long long bimg = row_ok ? tok / a.L : 0;
+    // epi_mode (chosen on the host): 1 = fp32 staging (LayerNorm / fp32 result / residual, whole row in this tile),
+    // 0 = 16-bit staging, 2 = direct per-row stores (odd widths such as the 3-channel image head)
+    if (EPI == EPI_BIAS_ACT && a.epi_mode == 2) {
+      const long long tok = s_tok[row];
       for (int c0 = 0; c0 < BN; c0 += 32) {
+        if (n0 + c0 >= a.N) break;
         tmem_ld32(trow + c0, v);
         tmem_ld_wait();
-        if (!row_ok) continue;
+        if (tok < 0) continue;
         float o[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          const int c = c0 + j;
-          float val = 0.f;
-          if (c < C) {
-            val = (__uint_as_float(v[j]) + a.bias[c] - mean) * rstd * a.gamma[c] + a.beta[c];
-            val = val * a.res_scale + a.res_f32[tok * a.ldr + c];
-            if (a.cab_y) val += __bfloat162float(a.cab_y[tok * a.ld_caby + c]) * a.cab_gate[bimg * C + c];
-          }
-          o[j] = val;
+          const int n = n0 + c0 + j;
+          float val = apply_act(__uint_as_float(v[j]) + (n < a.N ? __ldg(a.bias + n) : 0.f), a.act, a.slope);
+          if (a.res_f32 && n < a.N_f32) val += __ldg(a.res_f32 + tok * a.ldr + n);
+          o[j] = (n < a.N) ? val : 0.f;
+          if (a.out_f32 && n < a.N_f32) a.out_f32[tok * a.ldo_f32 + n] = o[j];
         }
+        if (out16) {
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const int c = c0 + j;
-          if (c + 3 < C) {
-            *reinterpret_cast<float4*>(a.out_f32 + tok * a.ldo_f32 + c) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
-          } else {
-            for (int e = 0; e < 4; ++e)
-              if (c + e < C) a.out_f32[tok * a.ldo_f32 + c + e] = o[j + e];
+          for (int j = 0; j < 32; j += 8)
+            if (n0 + c0 + j < a.ldo_bf16)
+              *reinterpret_cast<uint4*>(out16 + tok * a.ldo_bf16 + n0 + c0 + j) =
+                  make_uint4(pack16(o[j], o[j + 1], fmt), pack16(o[j + 2], o[j + 3], fmt), pack16(o[j + 4], o[j + 5], fmt),
+                             pack16(o[j + 6], o[j + 7], fmt));
+        }
+      }
+    } else if (a.epi_mode == 1) {
+      const int Cw = (EPI == EPI_LN) ? a.C : a.N_f32;  // real fp32 columns of this tile row (n0 == 0 when wide)
+      const int pitch = stage_pitch32(Cw);
+      float* stg = reinterpret_cast<float*>(smem);
+      // ---------------- phase A
+      if (EPI == EPI_LN) {
+        float sum = 0.f;
+        for (int c0 = 0; c0 < Cw; c0 += 32) {
+          tmem_ld32(trow + c0, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (c0 + j < Cw) sum += __uint_as_float(v[j]) + __ldg(a.bias + c0 + j);
+        }
+        const float mean = sum / (float)Cw;
+        float var = 0.f;
+        for (int c0 = 0; c0 < Cw; c0 += 32) {
+          tmem_ld32(trow + c0, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (c0 + j < Cw) {
+              const float d = __uint_as_float(v[j]) + __ldg(a.bias + c0 + j) - mean;
+              var = fmaf(d, d, var);
+            }
+        }
+        const float rstd = rsqrtf(var / (float)Cw + a.eps);
+        for (int c0 = 0; c0 < Cw; c0 += 32) {
+          tmem_ld32(trow + c0, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float o4[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int c = c0 + j + e;
+              o4[e] = (c < Cw) ? ((__uint_as_float(v[j + e]) + __ldg(a.bias + c) - mean) * rstd * __ldg(a.gamma + c) +
+                                  __ldg(a.beta + c)) * a.res_scale
+                               : 0.f;
+            }
+            if (c0 + j < pitch) *reinterpret_cast<float4*>(stg + row * pitch + c0 + j) = make_float4(o4[0], o4[1], o4[2], o4[3]);
           }
         }
-        if (c0 < a.ldo_bf16) {  // operand copy, zero in the pad channels
+      } else {
+        for (int c0 = 0; c0 < Cw; c0 += 32) {
+          tmem_ld32(trow + c0, v);
+          tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            uint4 pk = make_uint4(pack_bf16(o[j], o[j + 1]), pack_bf16(o[j + 2], o[j + 3]), pack_bf16(o[j + 4], o[j + 5]),
-                                  pack_bf16(o[j + 6], o[j + 7]));
-            if (c0 + j < a.ldo_bf16) *reinterpret_cast<uint4*>(a.out_bf16 + tok * a.ldo_bf16 + c0 + j) = pk;
+          for (int j = 0; j < 32; j += 4) {
+            float o4[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int n = c0 + j + e;
+              o4[e] = (n < a.N) ? apply_act(__uint_as_float(v[j + e]) + __ldg(a.bias + n), a.act, a.slope) : 0.f;
+            }
+            if (c0 + j < pitch) *reinterpret_cast<float4*>(stg + row * pitch + c0 + j) = make_float4(o4[0], o4[1], o4[2], o4[3]);
+          }
+        }
+      }
+      tcgen05_fence_before();
+      epi_barrier();
+      // ---------------- phase B: row-major streaming, 4 columns per thread, warp = row group.
+      // All global loads of a batch of RB rows are issued before any store (the compiler cannot prove the output
+      // and residual pointers distinct, so interleaving would serialise every row on a DRAM round trip).
+      const int C4 = Cw >> 2;                              // float4 items with real data
+      const int P4 = out16 ? (int)(a.ldo_bf16 >> 2) : C4;  // the 16-bit copy is written up to its (zero) pad
+      const int ew = et >> 5;
+      const bool has_cab = (EPI == EPI_LN) && a.cab_y != nullptr;
+      const uint16_t* caby = reinterpret_cast<const uint16_t*>(a.cab_y);
+      constexpr int RB = 8;
+      for (int cbase = 0; cbase < P4; cbase += 32) {
+        const int c4 = cbase + lane;
+        const bool col_real = c4 < C4, col_any = c4 < P4;
+        for (int rb = 0; rb < 32; rb += RB) {  // this warp's rows: ew, ew + 4, ...
+          long long tok[RB];
+          float4 rr[RB], gg[RB];
+          uint2 cy[RB];
+#pragma unroll
+          for (int i = 0; i < RB; ++i) {
+            tok[i] = s_tok[ew + 4 * (rb + i)];
+            rr[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            gg[i] = rr[i];
+            cy[i] = make_uint2(0u, 0u);
+            if (tok[i] >= 0 && col_real) {
+              if (a.res_f32) rr[i] = __ldg(reinterpret_cast<const float4*>(a.res_f32 + tok[i] * a.ldr + c4 * 4));
+              if (has_cab) {
+                cy[i] = __ldg(reinterpret_cast<const uint2*>(caby + tok[i] * a.ld_caby + c4 * 4));
+                gg[i] = __ldg(reinterpret_cast<const float4*>(a.cab_gate + (tok[i] / a.L) * Cw + c4 * 4));
+              }
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < RB; ++i) {
+            if (tok[i] < 0 || !col_any) continue;
+            float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (col_real) {
+              val = *reinterpret_cast<const float4*>(stg + (ew + 4 * (rb + i)) * pitch + c4 * 4);
+              val.x += rr[i].x, val.y += rr[i].y, val.z += rr[i].z, val.w += rr[i].w;
+              if (has_cab) {
+                const float2 c01 = unpack16(cy[i].x, fmt), c23 = unpack16(cy[i].y, fmt);
+                val.x = fmaf(c01.x, gg[i].x, val.x), val.y = fmaf(c01.y, gg[i].y, val.y);
+                val.z = fmaf(c23.x, gg[i].z, val.z), val.w = fmaf(c23.y, gg[i].w, val.w);
+              }
+              if (a.out_f32) *reinterpret_cast<float4*>(a.out_f32 + tok[i] * a.ldo_f32 + c4 * 4) = val;
+            }
+            if (out16)
+              *reinterpret_cast<uint2*>(out16 + tok[i] * a.ldo_bf16 + c4 * 4) =
+                  make_uint2(pack16(val.x, val.y, fmt), pack16(val.z, val.w, fmt));
           }
         }
       }
     } else {
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        if (n0 + c0 >= a.N) break;  // warp-uniform
+      // ---------------- 16-bit outputs only: phase A packs into a [128][BN + 8] tile
+      constexpr int P16 = BN + 8;
+      uint16_t* stg = reinterpret_cast<uint16_t*>(smem);
+      const int ncols = min(BN, a.N - n0);  // columns of this tile that exist (multiple of 32)
+      for (int c0 = 0; c0 < ncols; c0 += 32) {
         tmem_ld32(trow + c0, v);
         tmem_ld_wait();
-        if (!row_ok) continue;
         float o[32];
         if (EPI == EPI_QKV) {
           const int slot = (n0 + c0) >> 5;
           float ss = 0.f;
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            o[j] = __uint_as_float(v[j]) + a.bias[n0 + c0 + j];
+            o[j] = __uint_as_float(v[j]) + __ldg(a.bias + n0 + c0 + j);
             ss = fmaf(o[j], o[j], ss);
           }
-          const float sc = a.slot_scale[slot];
+          const float sc = __ldg(a.slot_scale + slot);
           const float mul = sc > 0.f ? sc / fmaxf(sqrtf(ss), 1e-12f) : 1.0f;  // scale <= 0 marks a value slot
 #pragma unroll
           for (int j = 0; j < 32; ++j) o[j] *= mul;
         } else {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int n = n0 + c0 + j;
-            float val = __uint_as_float(v[j]) + (n < a.N ? a.bias[n] : 0.f);
-            val = apply_act(val, a.act, a.slope);
-            if (a.res_f32 && n < a.N_f32) val += a.res_f32[tok * a.ldr + n];
-            o[j] = (n < a.N) ? val : 0.f;
-          }
+          for (int j = 0; j < 32; ++j) o[j] = apply_act(__uint_as_float(v[j]) + __ldg(a.bias + n0 + c0 + j), a.act, a.slope);
         }
-        if (a.out_bf16) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            if (n0 + c0 + j < a.ldo_bf16) {
-              uint4 pk = make_uint4(pack_bf16(o[j], o[j + 1]), pack_bf16(o[j + 2], o[j + 3]),
-                                    pack_bf16(o[j + 4], o[j + 5]), pack_bf16(o[j + 6], o[j + 7]));
-              *reinterpret_cast<uint4*>(a.out_bf16 + tok * a.ldo_bf16 + n0 + c0 + j) = pk;
-            }
-          }
-        }
-        if (EPI == EPI_BIAS_ACT && a.out_f32) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int n = n0 + c0 + j;
-            if (n < a.N_f32) a.out_f32[tok * a.ldo_f32 + n] = o[j];
-          }
-        }
+        for (int j = 0; j < 32; j += 8)
+          *reinterpret_cast<uint4*>(stg + row * P16 + c0 + j) =
+              make_uint4(pack16(o[j], o[j + 1], fmt), pack16(o[j + 2], o[j + 3], fmt), pack16(o[j + 4], o[j + 5], fmt),
+                         pack16(o[j + 6], o[j + 7], fmt));
+      }
+      tcgen05_fence_before();
+      epi_barrier();
+      const int nvec = min((long long)ncols, a.ldo_bf16 - n0) >> 3;  // 16-byte vectors per row
+      const int ew = et >> 5;
+#pragma unroll 4
+      for (int r = ew; r < kBM; r += 4) {
+        const long long tok = s_tok[r];
+        if (tok < 0) continue;
+        for (int vv = lane; vv < nvec; vv += 32)
+          *reinterpret_cast<uint4*>(out16 + tok * a.ldo_bf16 + n0 + vv * 8) = *reinterpret_cast<const uint4*>(stg + r * P16 + vv * 8);
       }
     }
-    tcgen05_fence_before();
   }
   __syncthreads();
   if (warp == 1) {
@@ -275,11 +369,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // host side
 // -------------------------------------------------------------------------------------
 static int make_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-                    const cuuint32_t* box) {
+                    const cuuint32_t* box, int fmt) {
   EncodeTiledFn fn = encode_tiled_fn();
   if (!fn) return fail(GRL_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
   cuuint32_t ones[5] = {1, 1, 1, 1, 1};
-  CUresult rc = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes,
+  CUresult rc = fn(m, fmt == FMT_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes,
                    box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (rc != CUDA_SUCCESS) return fail(GRL_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)rc);
@@ -328,6 +422,19 @@ int launch_gemm_tc(const GemmTcProblem& p, GemmTcArgs a, cudaStream_t st) {
               p.npad);
   const bool conv = p.taps == 9;
   GRL_REQUIRE(p.taps == 1 || p.taps == 9, "gemm_tc: taps must be 1 or 9");
+  // Epilogue mode.  fp32 staging (LayerNorm, fp32 output, residual) needs the whole output row in one tile, 16-byte
+  // aligned fp32 rows and a tile that fits the staging area; anything else with an fp32 side takes the direct path.
+  a.epi_mode = 0;
+  if (p.epi == EPI_LN || (p.epi == EPI_BIAS_ACT && (a.out_f32 || a.res_f32))) {
+    const int cw = p.epi == EPI_LN ? a.C : a.N_f32;
+    const int cap = bn == 64 ? GemmSmem<64>::OFF_TOK : bn == 128 ? GemmSmem<128>::OFF_TOK : bn == 192 ? GemmSmem<192>::OFF_TOK
+                                                                                                     : GemmSmem<256>::OFF_TOK;
+    const bool ok = p.npad <= bn && cw > 0 && cw % 4 == 0 && kBM * stage_pitch32(cw) * 4 <= cap &&
+                    (!a.out_f32 || a.ldo_f32 % 4 == 0) && (!a.res_f32 || a.ldr % 4 == 0) &&
+                    (!a.out_bf16 || a.ldo_bf16 % 4 == 0);
+    GRL_REQUIRE(ok || p.epi != EPI_LN, "gemm_tc: LayerNorm epilogue needs C %% 4 == 0 and C <= 188 (got %d)", cw);
+    a.epi_mode = ok ? 1 : 2;
+  }
   CUtensorMap tmA, tmB;
   int rc;
   dim3 grid;
@@ -337,7 +444,7 @@ int launch_gemm_tc(const GemmTcProblem& p, GemmTcArgs a, cudaStream_t st) {
     cuuint64_t dims[4] = {(cuuint64_t)p.kpad, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.B};
     cuuint64_t str[3] = {(cuuint64_t)p.kpad * 2, (cuuint64_t)p.W * p.kpad * 2, (cuuint64_t)p.H * p.W * p.kpad * 2};
     cuuint32_t box[4] = {(cuuint32_t)kBK, (cuuint32_t)kTW, (cuuint32_t)kTH, 1};
-    if ((rc = make_map(&tmA, p.x, 4, dims, str, box)) != GRL_OK) return rc;
+    if ((rc = make_map(&tmA, p.x, 4, dims, str, box, a.fmt)) != GRL_OK) return rc;
     a.H = p.H, a.W = p.W;
     a.tiles_x = ceil_div(p.W, kTW), a.tiles_y = ceil_div(p.H, kTH);
     a.M = (long long)p.B * p.H * p.W;
@@ -346,7 +453,7 @@ int launch_gemm_tc(const GemmTcProblem& p, GemmTcArgs a, cudaStream_t st) {
     cuuint64_t dims[2] = {(cuuint64_t)p.kpad, (cuuint64_t)p.M};
     cuuint64_t str[1] = {(cuuint64_t)p.kpad * 2};
     cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)kBM};
-    if ((rc = make_map(&tmA, p.x, 2, dims, str, box)) != GRL_OK) return rc;
+    if ((rc = make_map(&tmA, p.x, 2, dims, str, box, a.fmt)) != GRL_OK) return rc;
     a.M = p.M;
     grid = dim3((unsigned)ceil_div(p.M, kBM), ceil_div(p.npad, bn));
   }
@@ -355,7 +462,7 @@ int launch_gemm_tc(const GemmTcProblem& p, GemmTcArgs a, cudaStream_t st) {
     cuuint64_t dims[2] = {(cuuint64_t)p.kpad * p.taps, (cuuint64_t)p.npad};
     cuuint64_t str[1] = {(cuuint64_t)p.kpad * p.taps * 2};
     cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)bn};
-    if ((rc = make_map(&tmB, p.w, 2, dims, str, box)) != GRL_OK) return rc;
+    if ((rc = make_map(&tmB, p.w, 2, dims, str, box, a.fmt)) != GRL_OK) return rc;
   }
   switch (p.epi) {
     case EPI_BIAS_ACT:

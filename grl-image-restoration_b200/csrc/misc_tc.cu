@@ -8,8 +8,8 @@ namespace grl {
 namespace tc {
 
 // fp32 (M, C) -> bf16 (M, Cpad), zero in [C, Cpad).  Each thread converts 8 channels (one 16-byte store).
-__global__ void pack_bf16_kernel(const float* __restrict__ x, long long ldx, __nv_bfloat16* __restrict__ y, long long M,
-                                 int C, int Cpad) {
+__global__ void pack_bf16_kernel(const float* __restrict__ x, long long ldx, uint16_t* __restrict__ y, long long M,
+                                 int C, int Cpad, int fmt) {
   const int per_row = Cpad / 8;
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= M * per_row) return;
@@ -19,22 +19,22 @@ __global__ void pack_bf16_kernel(const float* __restrict__ x, long long ldx, __n
 #pragma unroll
   for (int e = 0; e < 8; ++e) v[e] = (c0 + e < C) ? x[m * ldx + c0 + e] : 0.f;
   *reinterpret_cast<uint4*>(y + m * Cpad + c0) =
-      make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+      make_uint4(pack16(v[0], v[1], fmt), pack16(v[2], v[3], fmt), pack16(v[4], v[5], fmt), pack16(v[6], v[7], fmt));
 }
 
 // bf16 (M, ld) -> fp32 (M, C)
-__global__ void unpack_bf16_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, int x_off, float* __restrict__ y,
-                                   long long ldy, long long M, int C) {
+__global__ void unpack_bf16_kernel(const uint16_t* __restrict__ x, long long ldx, int x_off, float* __restrict__ y,
+                                   long long ldy, long long M, int C, int fmt) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= M * C) return;
   const long long m = i / C;
   const int c = (int)(i - m * C);
-  y[m * ldy + c] = __bfloat162float(x[m * ldx + x_off + c]);
+  y[m * ldy + c] = unpack16_one(x[m * ldx + x_off + c], fmt);
 }
 
 // AvgPool2d(df) on bf16 channels-last data, fp32 accumulation; 8 channels per thread.
-__global__ void avgpool_bf16_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int B, int H,
-                                    int W, int Cpad, int df) {
+__global__ void avgpool_bf16_kernel(const uint16_t* __restrict__ x, uint16_t* __restrict__ y, int B, int H,
+                                    int W, int Cpad, int df, int fmt) {
   const int Ho = H / df, Wo = W / df, per = Cpad / 8;
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)B * Ho * Wo * per) return;
@@ -48,28 +48,29 @@ __global__ void avgpool_bf16_kernel(const __nv_bfloat16* __restrict__ x, __nv_bf
   for (int dy = 0; dy < df; ++dy)
     for (int dx = 0; dx < df; ++dx) {
       const uint4 raw = *reinterpret_cast<const uint4*>(x + (((long long)b * H + yo * df + dy) * W + xo * df + dx) * Cpad + c0);
-      const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(&raw);
+      const uint32_t* p = reinterpret_cast<const uint32_t*>(&raw);
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        const float2 f = __bfloat1622float2(p[e]);
+        const float2 f = unpack16(p[e], fmt);
         s[2 * e] += f.x;
         s[2 * e + 1] += f.y;
       }
     }
   const float inv = 1.f / (float)(df * df);
-  *reinterpret_cast<uint4*>(y + i * 8) = make_uint4(pack_bf16(s[0] * inv, s[1] * inv), pack_bf16(s[2] * inv, s[3] * inv),
-                                                    pack_bf16(s[4] * inv, s[5] * inv), pack_bf16(s[6] * inv, s[7] * inv));
+  *reinterpret_cast<uint4*>(y + i * 8) =
+      make_uint4(pack16(s[0] * inv, s[1] * inv, fmt), pack16(s[2] * inv, s[3] * inv, fmt),
+                 pack16(s[4] * inv, s[5] * inv, fmt), pack16(s[6] * inv, s[7] * inv, fmt));
 }
 
 // Deterministic partial channel sums of bf16 features y (B, L, ld): partial (B, chunks, C) fp32.
 constexpr int kPoolRowsTc = 512;
-__global__ void channel_partial_bf16_kernel(const __nv_bfloat16* __restrict__ y, long long L, long long ld, int C,
+__global__ void channel_partial_bf16_kernel(const uint16_t* __restrict__ y, long long L, long long ld, int C, int fmt,
                                             float* __restrict__ partial, int chunks) {
   const int b = blockIdx.y, ch = blockIdx.x;
   const long long r0 = (long long)ch * kPoolRowsTc, r1 = min(L, r0 + kPoolRowsTc);
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float s = 0.f;
-    for (long long r = r0; r < r1; ++r) s += __bfloat162float(y[((long long)b * L + r) * ld + c]);
+    for (long long r = r0; r < r1; ++r) s += unpack16_one(y[((long long)b * L + r) * ld + c], fmt);
     partial[((long long)b * chunks + ch) * C + c] = s;
   }
 }
@@ -94,35 +95,35 @@ __global__ void slot_scale_kernel(const float* __restrict__ ls_w, const float* _
   }
 }
 
-int launch_pack_bf16(const float* x, long long ldx, __nv_bfloat16* y, long long M, int C, int Cpad, cudaStream_t st) {
+int launch_pack_bf16(const float* x, long long ldx, void* y, long long M, int C, int Cpad, int fmt, cudaStream_t st) {
   GRL_REQUIRE(Cpad % 8 == 0 && Cpad >= C, "pack_bf16: bad padding %d for %d channels", Cpad, C);
   if (M == 0) return GRL_OK;
-  pack_bf16_kernel<<<ceil_div(M * (Cpad / 8), 256), 256, 0, st>>>(x, ldx, y, M, C, Cpad);
+  pack_bf16_kernel<<<ceil_div(M * (Cpad / 8), 256), 256, 0, st>>>(x, ldx, (uint16_t*)y, M, C, Cpad, fmt);
   GRL_LAUNCH_CHECK("pack_bf16_kernel");
   return GRL_OK;
 }
-int launch_unpack_bf16(const __nv_bfloat16* x, long long ldx, int x_off, float* y, long long ldy, long long M, int C,
+int launch_unpack_bf16(const void* x, long long ldx, int x_off, float* y, long long ldy, long long M, int C, int fmt,
                        cudaStream_t st) {
   if (M == 0) return GRL_OK;
-  unpack_bf16_kernel<<<ceil_div(M * C, 256), 256, 0, st>>>(x, ldx, x_off, y, ldy, M, C);
+  unpack_bf16_kernel<<<ceil_div(M * C, 256), 256, 0, st>>>((const uint16_t*)x, ldx, x_off, y, ldy, M, C, fmt);
   GRL_LAUNCH_CHECK("unpack_bf16_kernel");
   return GRL_OK;
 }
-int launch_avgpool_bf16(const __nv_bfloat16* x, __nv_bfloat16* y, int B, int H, int W, int Cpad, int df, cudaStream_t st) {
+int launch_avgpool_bf16(const void* x, void* y, int B, int H, int W, int Cpad, int df, int fmt, cudaStream_t st) {
   GRL_REQUIRE(df >= 1 && H % df == 0 && W % df == 0 && Cpad % 8 == 0, "avgpool_bf16: bad shape");
   long long total = (long long)B * (H / df) * (W / df) * (Cpad / 8);
   if (total == 0) return GRL_OK;
-  avgpool_bf16_kernel<<<ceil_div(total, 256), 256, 0, st>>>(x, y, B, H, W, Cpad, df);
+  avgpool_bf16_kernel<<<ceil_div(total, 256), 256, 0, st>>>((const uint16_t*)x, (uint16_t*)y, B, H, W, Cpad, df, fmt);
   GRL_LAUNCH_CHECK("avgpool_bf16_kernel");
   return GRL_OK;
 }
 size_t channel_partial_bf16_ws(int B, long long L, int C) { return sizeof(float) * (size_t)B * ceil_div(L, kPoolRowsTc) * C; }
-int launch_channel_partial_bf16(const __nv_bfloat16* y, int B, long long L, long long ld, int C, float* partial,
+int launch_channel_partial_bf16(const void* y, int B, long long L, long long ld, int C, int fmt, float* partial,
                                 int* chunks_out, cudaStream_t st) {
   const int chunks = ceil_div(L, kPoolRowsTc);
   *chunks_out = chunks;
   if (B == 0) return GRL_OK;
-  channel_partial_bf16_kernel<<<dim3(chunks, B), 256, 0, st>>>(y, L, ld, C, partial, chunks);
+  channel_partial_bf16_kernel<<<dim3(chunks, B), 256, 0, st>>>((const uint16_t*)y, L, ld, C, fmt, partial, chunks);
   GRL_LAUNCH_CHECK("channel_partial_bf16_kernel");
   return GRL_OK;
 }

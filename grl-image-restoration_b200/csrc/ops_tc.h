@@ -12,15 +12,17 @@ namespace tc {
 enum { EPI_BIAS_ACT = 0, EPI_QKV = 1, EPI_LN = 2 };
 
 struct GemmTcArgs {
+  int fmt;  // operand / 16-bit activation format: 0 = fp16, 1 = bf16
   // filled by launch_gemm_tc
   long long M;
   int nk, taps;
   int H, W, tiles_x, tiles_y;
+  int epi_mode;  // 0 = 16-bit staging, 1 = fp32 staging, 2 = direct
   // epilogue
   int N;      // columns computed/stored as bf16 (zero beyond the real outputs)
   int N_f32;  // real outputs (fp32 store / residual width)
   const float* bias;  // (npad), zero in the pad
-  __nv_bfloat16* out_bf16;
+  void* out_bf16;  // 16-bit output (fp16 or bf16 per fmt)
   long long ldo_bf16;
   float* out_f32;
   long long ldo_f32;
@@ -35,7 +37,7 @@ struct GemmTcArgs {
   const float* gamma;
   const float* beta;
   float eps, res_scale;
-  const __nv_bfloat16* cab_y;
+  const void* cab_y;  // 16-bit
   long long ld_caby;
   const float* cab_gate;
   long long L;
@@ -53,6 +55,7 @@ int launch_gemm_tc(const GemmTcProblem& p, GemmTcArgs a, cudaStream_t st);
 
 // Fused attention on packed bf16 head slots (32 wide).  See attn_tc.cu.
 struct AttnTcArgs {
+  int fmt;  // 0 = fp16, 1 = bf16 (all 16-bit operands and outputs)
   GrlGrid gq, gk;
   const __nv_bfloat16* q;
   long long ldq;  // elements per token row
@@ -80,12 +83,12 @@ int launch_attn_tc(const AttnTcArgs& a, cudaStream_t st);
 
 namespace grl {
 namespace tc {
-int launch_pack_bf16(const float* x, long long ldx, __nv_bfloat16* y, long long M, int C, int Cpad, cudaStream_t st);
-int launch_unpack_bf16(const __nv_bfloat16* x, long long ldx, int x_off, float* y, long long ldy, long long M, int C,
+int launch_pack_bf16(const float* x, long long ldx, void* y, long long M, int C, int Cpad, int fmt, cudaStream_t st);
+int launch_unpack_bf16(const void* x, long long ldx, int x_off, float* y, long long ldy, long long M, int C, int fmt,
                        cudaStream_t st);
-int launch_avgpool_bf16(const __nv_bfloat16* x, __nv_bfloat16* y, int B, int H, int W, int Cpad, int df, cudaStream_t st);
+int launch_avgpool_bf16(const void* x, void* y, int B, int H, int W, int Cpad, int df, int fmt, cudaStream_t st);
 size_t channel_partial_bf16_ws(int B, long long L, int C);
-int launch_channel_partial_bf16(const __nv_bfloat16* y, int B, long long L, long long ld, int C, float* partial,
+int launch_channel_partial_bf16(const void* y, int B, long long L, long long ld, int C, int fmt, float* partial,
                                 int* chunks_out, cudaStream_t st);
 int launch_slot_scale(const float* ls_w, const float* ls_s1, const float* ls_s2, int hw, int hs, float* out,
                       cudaStream_t st);

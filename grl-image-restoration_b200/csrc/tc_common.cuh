@@ -5,6 +5,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -145,6 +146,24 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
+}
+// Operand formats of the tensor-core path: FMT_F16 (default: 11-bit mantissa, saturating converts) or FMT_BF16.
+enum : int { FMT_F16 = 0, FMT_BF16 = 1 };
+__device__ __forceinline__ uint32_t pack_f16(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+__device__ __forceinline__ uint32_t pack16(float lo, float hi, int fmt) {
+  return fmt == FMT_BF16 ? pack_bf16(lo, hi) : pack_f16(lo, hi);
+}
+__device__ __forceinline__ float2 unpack16(uint32_t v, int fmt) {
+  if (fmt == FMT_BF16) return make_float2(__uint_as_float(v << 16), __uint_as_float(v & 0xFFFF0000u));
+  return __half22float2(*reinterpret_cast<const __half2*>(&v));
+}
+__device__ __forceinline__ float unpack16_one(uint16_t v, int fmt) {
+  if (fmt == FMT_BF16) return __uint_as_float((uint32_t)v << 16);
+  return __half2float(*reinterpret_cast<const __half*>(&v));
 }
 
 // ------------------------------------------------------------------ host: tensor maps without linking libcuda

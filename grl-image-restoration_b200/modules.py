@@ -374,17 +374,17 @@ class EfficientMixAttnTransformerBlock(nn.Module):
             "mask_w2a": a[f"mask_{d}_w2a"] if self.stripe_shift else None,
         }
 
-    precision = "fp32"  # "fp32": exact-parity SIMT kernels; "bf16": fused tcgen05 path (tc.py)
+    precision = "fp32"  # "fp32": exact-parity SIMT kernels; "fp16" / "bf16": fused tcgen05 path (tc.py)
 
     @torch.no_grad()
     def forward(self, x, x_size, all_table_index_mask):
         t = self._get_table_index_mask(all_table_index_mask)
-        if self.precision == "bf16":
+        if self.precision != "fp32":
             from . import tc
 
             K.capi.require_device(x)
             x32 = x if x.is_contiguous() else x.contiguous()
-            y32, y16 = tc.block_plan(self).run(self, x32, getattr(x, "_grl_bf16", None), x_size, t)
+            y32, y16 = tc.block_plan(self, tc.FMT[self.precision]).run(self, x32, getattr(x, "_grl_bf16", None), x_size, t)
             y32._grl_bf16 = y16  # operand copy for the next GEMM (saves a re-pack per block)
             return y32
         u = self.attn(x, x_size, t)
@@ -509,16 +509,17 @@ class TransformerStage(nn.Module):
             res = blk(res, x_size, table_index_mask)
         B, L, C = x.shape
         H, W = x_size
-        if len(self.blocks) and self.blocks[0].precision == "bf16":
+        if len(self.blocks) and self.blocks[0].precision != "fp32":
             from . import tc
 
+            fmt = tc.FMT[self.blocks[0].precision]
             cpad = tc.round_up(C, 64)
             r16 = getattr(res, "_grl_bf16", None)
-            if r16 is None:
-                r16 = tc.pack_rows(res.contiguous(), cpad)
-            plan = tc.conv_plan(self, "conv", self.conv, cpad)
+            if r16 is None or r16.dtype != tc.DTYPE[fmt]:
+                r16 = tc.pack_rows(res.contiguous(), cpad, fmt)
+            plan = tc.conv_plan(self, "conv", self.conv, cpad, fmt)
             out32 = torch.empty(B, L, C, device=x.device, dtype=torch.float32)
-            out16 = torch.empty(B, L, cpad, device=x.device, dtype=torch.bfloat16)
+            out16 = torch.empty(B, L, cpad, device=x.device, dtype=tc.DTYPE[fmt])
             tc.conv3x3(r16.view(B, H, W, cpad), plan.w, plan.b, cpad, plan.npad, n_store=cpad, n_real=C, out_bf16=out16,
                        out_f32=out32, res_f32=x.contiguous())
             out32._grl_bf16 = out16
@@ -624,16 +625,18 @@ class GRL(nn.Module):
 
     # ---- precision ----------------------------------------------------------------------------
     def set_precision(self, precision):
-        """"fp32": exact-parity kernels (<= 1e-3 vs the reference); "bf16": tcgen05 tensor-core path (PSNR-gated);
-        "auto": bf16 when the architecture fits the tensor-core kernels (head_dim <= 32, C % 4 == 0)."""
+        """"fp32": exact-parity kernels (<= 1e-3 vs the reference).  "fp16" / "bf16": tcgen05 tensor-core path with
+        that MMA operand format (fp32 accumulation, residual stream, LayerNorm and softmax statistics); fp16 operands
+        (11-bit mantissa) are what meets the 0.01 dB PSNR gate, bf16 is provided for range-critical checkpoints.
+        "auto": fp16 when the architecture fits the tensor-core kernels (head_dim <= 32, C % 4 == 0), else fp32."""
         from . import tc
 
-        if precision not in ("fp32", "bf16", "auto"):
-            raise ValueError(f"precision must be fp32 / bf16 / auto, got {precision!r}")
+        if precision not in ("fp32", "fp16", "bf16", "auto"):
+            raise ValueError(f"precision must be fp32 / fp16 / bf16 / auto, got {precision!r}")
         ok = all(tc.supported(self.embed_dim, b.num_heads_w, b.num_heads_s) for l in self.layers for b in l.blocks)
-        if precision == "bf16" and not ok:
-            raise RuntimeError("this architecture is outside the bf16 tensor-core path (head_dim > 32 or C % 4 != 0)")
-        self.precision = "bf16" if (precision in ("bf16", "auto") and ok) else "fp32"
+        if precision in ("fp16", "bf16") and not ok:
+            raise RuntimeError("this architecture is outside the tensor-core path (head_dim > 32 or C % 4 != 0)")
+        self.precision = ("fp16" if precision == "auto" else precision) if (precision != "fp32" and ok) else "fp32"
         for l in self.layers:
             for b in l.blocks:
                 b.precision = self.precision
@@ -737,16 +740,17 @@ class GRL(nn.Module):
         from . import tc
 
         dev = x.device
+        fmt = tc.FMT[self.precision]
         B, Cin, Hp, Wp = x.shape
         C = self.embed_dim
         cpad = tc.round_up(C, 64)
         xc = x.permute(0, 2, 3, 1).contiguous()
-        x16 = tc.pack_rows(xc, 64)
+        x16 = tc.pack_rows(xc, 64, fmt)
 
-        def conv(name, module, inp16, cin_pad, *, act=K.ACT_NONE, slope=0.0, res=None, want_f32=False):
-            plan = tc.conv_plan(self, name, module, cin_pad)
+        def conv(name, module, inp16, cin_pad, *, act=K.ACT_NONE, slope=0.0, res=None, want_f32=False, want16=True):
+            plan = tc.conv_plan(self, name, module, cin_pad, fmt)
             b, h, w, _ = inp16.shape
-            o16 = torch.empty(b, h, w, plan.npad, device=dev, dtype=torch.bfloat16)
+            o16 = torch.empty(b, h, w, plan.npad, device=dev, dtype=tc.DTYPE[fmt]) if want16 else None
             o32 = torch.empty(b, h, w, plan.cout, device=dev, dtype=torch.float32) if want_f32 else None
             tc.conv3x3(inp16, plan.w, plan.b, cin_pad, plan.npad, n_store=plan.npad, n_real=plan.cout, act=act, slope=slope,
                        out_bf16=o16, out_f32=o32, res_f32=res)
@@ -759,7 +763,7 @@ class GRL(nn.Module):
         for layer in self.layers:
             t = layer(t, (Hp, Wp), tim)
         t = K.ln_residual(None, t, self.norm_end.weight, self.norm_end.bias, self.norm_end.eps)
-        t16 = tc.pack_rows(t, cpad).view(B, Hp, Wp, cpad)
+        t16 = tc.pack_rows(t, cpad, fmt).view(B, Hp, Wp, cpad)
         last_f32 = self.upsampler not in ("pixelshuffle", "nearest+conv")
         body16, body32 = conv("conv_after_body", self.conv_after_body, t16, cpad, res=f32, want_f32=last_f32)
         if self.upsampler == "pixelshuffle":
@@ -769,10 +773,10 @@ class GRL(nn.Module):
                     u16, _ = conv(f"upsample.up.{i}", m, u16, u16.shape[-1])
                 else:
                     u16 = pixel_shuffle_cl(u16[..., : u16.shape[-1]], m.upscale_factor).contiguous()
-            _, y = conv("conv_last", self.conv_last, u16, u16.shape[-1], want_f32=True)
+            _, y = conv("conv_last", self.conv_last, u16, u16.shape[-1], want_f32=True, want16=False)
         elif self.upsampler == "pixelshuffledirect":
             m = self.upsample.up[0]
-            _, y = conv("upsample.up.0", m, body16, cpad, want_f32=True)
+            _, y = conv("upsample.up.0", m, body16, cpad, want_f32=True, want16=False)
             y = pixel_shuffle_cl(y, self.upsample.up[1].upscale_factor)
         elif self.upsampler == "nearest+conv":
             u16, _ = conv("conv_before_upsample", self.conv_before_upsample[0], body16, cpad, act=K.ACT_LEAKY, slope=0.01)
@@ -780,10 +784,10 @@ class GRL(nn.Module):
             u16, _ = conv("conv_up1", self.conv_up1, up(u16), u16.shape[-1], act=K.ACT_LEAKY, slope=0.2)
             u16, _ = conv("conv_up2", self.conv_up2, up(u16), u16.shape[-1], act=K.ACT_LEAKY, slope=0.2)
             u16, _ = conv("conv_hr", self.conv_hr, u16, u16.shape[-1], act=K.ACT_LEAKY, slope=0.2)
-            _, y = conv("conv_last", self.conv_last, u16, u16.shape[-1], want_f32=True)
+            _, y = conv("conv_last", self.conv_last, u16, u16.shape[-1], want_f32=True, want16=False)
         else:
             res = xc if self.in_channels == self.out_channels else None
-            _, y = conv("conv_last", self.conv_last, body16, cpad, res=res, want_f32=True)
+            _, y = conv("conv_last", self.conv_last, body16, cpad, res=res, want_f32=True, want16=False)
         y = y.permute(0, 3, 1, 2) / self.img_range + self.mean
         return y[:, :, : H * self.upscale, : W * self.upscale].contiguous()
 
@@ -799,7 +803,7 @@ class GRL(nn.Module):
         x = self.check_image_size(x)
         self.mean = self.mean.type_as(x)
         x = ((x - self.mean) * self.img_range).float()
-        if self.precision == "bf16":
+        if self.precision != "fp32":
             return self._forward_bf16(x, H, W)
         xc = x.permute(0, 2, 3, 1).contiguous()  # channels-last from here on
         first = self._conv("conv_first", self.conv_first, xc)

@@ -19,6 +19,12 @@ from . import geometry as G
 LOG2E = 1.4426950408889634
 EPI_BIAS_ACT, EPI_QKV, EPI_LN = 0, 1, 2
 SLOT = 32
+FMT = {"fp16": 0, "bf16": 1}
+DTYPE = {0: torch.float16, 1: torch.bfloat16}
+
+
+def fmt_of(t):
+    return 1 if t.dtype == torch.bfloat16 else 0
 
 
 def round_up(a, b):
@@ -31,36 +37,36 @@ def supported(C, heads_w, heads_s):
             and heads_w <= 8 and heads_s <= 8)
 
 
-def _bf16(*shape, device, zero=False):
-    return (torch.zeros if zero else torch.empty)(*shape, device=device, dtype=torch.bfloat16)
+def _h16(*shape, device, fmt, zero=False):
+    return (torch.zeros if zero else torch.empty)(*shape, device=device, dtype=DTYPE[fmt])
 
 
-def pack_rows(x, cpad):
-    """fp32 (..., C) contiguous -> bf16 (..., cpad), zero padded."""
+def pack_rows(x, cpad, fmt=0):
+    """fp32 (..., C) contiguous -> 16-bit (..., cpad), zero padded."""
     C = x.shape[-1]
     M = x.numel() // C
-    y = _bf16(*x.shape[:-1], cpad, device=x.device)
-    capi.check(capi.lib().grl_tc_pack_bf16(capi.ptr(x), C, capi.ptr(y), M, C, cpad, capi.stream()))
+    y = _h16(*x.shape[:-1], cpad, device=x.device, fmt=fmt)
+    capi.check(capi.lib().grl_tc_pack16(capi.ptr(x), C, capi.ptr(y), M, C, cpad, fmt, capi.stream()))
     return y
 
 
 def unpack_rows(x16, C, off=0):
-    """bf16 (..., ld) -> fp32 (..., C) taking columns [off, off + C)."""
+    """16-bit (..., ld) -> fp32 (..., C) taking columns [off, off + C)."""
     ld = x16.shape[-1]
     M = x16.numel() // ld
     y = torch.empty(*x16.shape[:-1], C, device=x16.device, dtype=torch.float32)
-    capi.check(capi.lib().grl_tc_unpack_bf16(capi.ptr(x16), ld, off, capi.ptr(y), C, M, C, capi.stream()))
+    capi.check(capi.lib().grl_tc_unpack16(capi.ptr(x16), ld, off, capi.ptr(y), C, M, C, fmt_of(x16), capi.stream()))
     return y
 
 
-def _pad_matrix(w, npad, kpad, row_map=None, col_map=None):
-    """Scatter fp32 (N, K) into bf16 (npad, kpad): dest row row_map[i] <- src row i, dest col col_map[j] <- src col j."""
+def _pad_matrix(w, npad, kpad, row_map=None, col_map=None, fmt=0):
+    """Scatter fp32 (N, K) into 16-bit (npad, kpad): dest row row_map[i] <- src row i, dest col col_map[j] <- src col j."""
     N, Kd = w.shape
     out = torch.zeros(npad, kpad, device=w.device, dtype=torch.float32)
     r = torch.arange(N, device=w.device) if row_map is None else torch.as_tensor(row_map, device=w.device)
     c = torch.arange(Kd, device=w.device) if col_map is None else torch.as_tensor(col_map, device=w.device)
     out[r[:, None], c[None, :]] = w.detach().float()
-    return out.to(torch.bfloat16).contiguous()
+    return out.to(DTYPE[fmt]).contiguous()
 
 
 def _pad_vector(b, npad, row_map=None):
@@ -71,8 +77,8 @@ def _pad_vector(b, npad, row_map=None):
     return out
 
 
-def pack_conv(conv, cin_pad, npad):
-    """nn.Conv2d(3x3) weight (Cout, Cin, 3, 3) -> bf16 (npad, 9*cin_pad), k = (ky*3+kx)*cin_pad + c; bias fp32 (npad)."""
+def pack_conv(conv, cin_pad, npad, fmt=0):
+    """nn.Conv2d(3x3) weight (Cout, Cin, 3, 3) -> 16-bit (npad, 9*cin_pad), k = (ky*3+kx)*cin_pad + c; bias fp32 (npad)."""
     w = conv.weight.detach().float()
     co, ci = w.shape[:2]
     out = torch.zeros(npad, 9, cin_pad, device=w.device, dtype=torch.float32)
@@ -80,13 +86,16 @@ def pack_conv(conv, cin_pad, npad):
     bias = torch.zeros(npad, device=w.device, dtype=torch.float32)
     if conv.bias is not None:
         bias[:co] = conv.bias.detach().float()
-    return out.reshape(npad, 9 * cin_pad).to(torch.bfloat16).contiguous(), bias
+    return out.reshape(npad, 9 * cin_pad).to(DTYPE[fmt]).contiguous(), bias
 
 
 def gemm(x16, w16, bias, *, M=0, image=None, kpad, npad, taps=1, epi=EPI_BIAS_ACT, n_store=0, n_real=0, out_bf16=None,
          out_f32=None, res_f32=None, act=K.ACT_NONE, slope=0.0, slot_scale=None, C=0, gamma=None, beta=None, eps=1e-5,
          res_scale=1.0, cab_y=None, cab_gate=None, L=1):
     p = capi.GrlTcGemm()
+    if x16.dtype != w16.dtype:
+        raise RuntimeError("grl_b200: activation / weight operand formats differ")
+    p.fmt = fmt_of(x16)
     p.x, p.w, p.bias = x16.data_ptr(), w16.data_ptr(), bias.data_ptr()
     p.M = M
     if image is not None:
@@ -115,6 +124,7 @@ def gemm(x16, w16, bias, *, M=0, image=None, kpad, npad, taps=1, epi=EPI_BIAS_AC
 def attention(gq, gk, q, q_off, k, k_off, v, v_off, out, o_off, B, heads, bias, use_mask, v_dense=False,
               o_dense=False, tag="attn"):
     p = capi.GrlTcAttn()
+    p.fmt = fmt_of(q)
     p.gq, p.gk = gq, gk
     p.q, p.ldq, p.q_off = q.data_ptr(), q.shape[-1], q_off
     p.k, p.ldk, p.k_off = k.data_ptr(), k.shape[-1], k_off
@@ -149,8 +159,10 @@ def _version_key(module):
 class BlockPlan:
     """Packed weights + launch sequence of one EfficientMixAttnTransformerBlock."""
 
-    def __init__(self, blk):
-        self.key = _version_key(blk)
+    def __init__(self, blk, fmt):
+        self.key = (_version_key(blk), fmt)
+        self.fmt = fmt
+        self._const_key, self._consts = None, None
         at = blk.attn
         C = blk.dim
         c = C // 2
@@ -168,13 +180,13 @@ class BlockPlan:
                         rmap.append((slot_base + t * h + head) * SLOT + e)
         # source rows are already ordered (half, t, head, e) in the reference layout (efficient.py:150,:251,:362)
         self.n_qkv = self.nslots * SLOT
-        self.w_qkv = _pad_matrix(at.qkv.body.weight, self.n_qkv, self.cpad, row_map=rmap)
+        self.w_qkv = _pad_matrix(at.qkv.body.weight, self.n_qkv, self.cpad, row_map=rmap, fmt=fmt)
         self.b_qkv = _pad_vector(at.qkv.body.bias if at.qkv.body.bias is not None else torch.zeros(3 * C, device=at.qkv.body.weight.device), self.n_qkv, rmap)
         # --- anchor projection: dest row = head*32 + e
         amap = [head * SLOT + e for head in range(hs) for e in range(ds)]
         red = at.anchor.body[0].reduction
         self.n_anc = hs * SLOT
-        self.w_anc = _pad_matrix(red.weight, round_up(self.n_anc, 32), self.cpad, row_map=amap)
+        self.w_anc = _pad_matrix(red.weight, round_up(self.n_anc, 32), self.cpad, row_map=amap, fmt=fmt)
         self.b_anc = _pad_vector(red.bias, round_up(self.n_anc, 32), amap)
         self.anc_scale = torch.ones(hs, device=red.weight.device, dtype=torch.float32)
         self.df = at.anchor.body[0].down_factor
@@ -183,14 +195,14 @@ class BlockPlan:
                [(hw + head) * SLOT + e for head in range(hs) for e in range(ds)]
         self.k_proj = round_up((hw + hs) * SLOT, 64)
         self.n_ln = 64 if C <= 64 else 128 if C <= 128 else 192 if C <= 192 else 256
-        self.w_proj = _pad_matrix(at.proj.weight, self.n_ln, self.k_proj, col_map=cmap)
+        self.w_proj = _pad_matrix(at.proj.weight, self.n_ln, self.k_proj, col_map=cmap, fmt=fmt)
         self.b_proj = _pad_vector(at.proj.bias, self.n_ln)
         # --- MLP
         hid = blk.mlp.fc1.weight.shape[0]
         self.hid, self.hpad = hid, round_up(hid, 64)
-        self.w_fc1 = _pad_matrix(blk.mlp.fc1.weight, self.hpad, self.cpad)
+        self.w_fc1 = _pad_matrix(blk.mlp.fc1.weight, self.hpad, self.cpad, fmt=fmt)
         self.b_fc1 = _pad_vector(blk.mlp.fc1.bias, self.hpad)
-        self.w_fc2 = _pad_matrix(blk.mlp.fc2.weight, self.n_ln, self.hpad)
+        self.w_fc2 = _pad_matrix(blk.mlp.fc2.weight, self.n_ln, self.hpad, fmt=fmt)
         self.b_fc2 = _pad_vector(blk.mlp.fc2.bias, self.n_ln)
         # --- CAB
         self.cab = bool(blk.args.local_connection)
@@ -198,8 +210,8 @@ class BlockPlan:
             c0, c2 = blk.conv.cab[0], blk.conv.cab[2]
             self.cmid = c0.weight.shape[0]
             self.cmid_pad = round_up(self.cmid, 64)
-            self.w_cab1, self.b_cab1 = pack_conv(c0, self.cpad, self.cmid_pad)
-            self.w_cab2, self.b_cab2 = pack_conv(c2, self.cmid_pad, self.cpad)
+            self.w_cab1, self.b_cab1 = pack_conv(c0, self.cpad, self.cmid_pad, fmt)
+            self.w_cab2, self.b_cab2 = pack_conv(c2, self.cmid_pad, self.cpad, fmt)
             a1, a3 = blk.conv.cab[3].attention[1], blk.conv.cab[3].attention[3]
             self.ca = (a1.weight.detach().reshape(a1.weight.shape[0], -1).contiguous(), a1.bias.detach(),
                        a3.weight.detach().reshape(a3.weight.shape[0], -1).contiguous(), a3.bias.detach())
@@ -212,39 +224,46 @@ class BlockPlan:
         dev = x32.device
         at = blk.attn
         hw, hs, cpad = self.hw, self.hs, self.cpad
-        if x16 is None:
-            x16 = pack_rows(x32, cpad)
+        fmt = self.fmt
+        if x16 is None or x16.dtype != DTYPE[fmt]:
+            x16 = pack_rows(x32, cpad, fmt)
         lib = capi.lib()
-        # attention constants of this block
-        slot_scale = torch.empty(self.nslots, device=dev, dtype=torch.float32)
         wa, sa = at.window_attn, at.stripe_attn
-        capi.check(lib.grl_tc_slot_scale(capi.ptr(wa.attn_transform.logit_scale), capi.ptr(sa.attn_transform1.logit_scale),
-                                         capi.ptr(sa.attn_transform2.logit_scale), hw, hs, capi.ptr(slot_scale),
-                                         capi.stream()))
-        bias_w = bias_table_log2(wa.attn_transform, t["table_w"])
-        bias_1 = bias_table_log2(sa.attn_transform1, t["table_s"])
-        bias_2 = bias_table_log2(sa.attn_transform2, t["table_s"])
+        # attention constants of this block (slot scales + activated bias tables): functions of the parameters and
+        # the coordinate tables only, so they are cached until a parameter or the resolution changes
+        ckey = (self.key, t["table_w"].data_ptr(), t["table_s"].data_ptr(), t["table_s"].shape)
+        if self._const_key != ckey:
+            slot_scale = torch.empty(self.nslots, device=dev, dtype=torch.float32)
+            capi.check(lib.grl_tc_slot_scale(capi.ptr(wa.attn_transform.logit_scale),
+                                             capi.ptr(sa.attn_transform1.logit_scale),
+                                             capi.ptr(sa.attn_transform2.logit_scale), hw, hs, capi.ptr(slot_scale),
+                                             capi.stream()))
+            self._consts = (slot_scale, bias_table_log2(wa.attn_transform, t["table_w"]),
+                            bias_table_log2(sa.attn_transform1, t["table_s"]),
+                            bias_table_log2(sa.attn_transform2, t["table_s"]))
+            self._const_key = ckey
+        slot_scale, bias_w, bias_1, bias_2 = self._consts
         # projections
-        qkv = _bf16(B * L, self.n_qkv, device=dev)
+        qkv = _h16(B * L, self.n_qkv, device=dev, fmt=fmt)
         gemm(x16, self.w_qkv, self.b_qkv, M=B * L, kpad=cpad, npad=self.n_qkv, epi=EPI_QKV, n_store=self.n_qkv,
              out_bf16=qkv, slot_scale=slot_scale)
         df = self.df
-        pooled = _bf16(B, H // df, W // df, cpad, device=dev)
-        capi.check(lib.grl_tc_avgpool_bf16(capi.ptr(x16), capi.ptr(pooled), B, H, W, cpad, df, capi.stream()))
+        pooled = _h16(B, H // df, W // df, cpad, device=dev, fmt=fmt)
+        capi.check(lib.grl_tc_avgpool16(capi.ptr(x16), capi.ptr(pooled), B, H, W, cpad, df, fmt, capi.stream()))
         La = (H // df) * (W // df)
         n_anc = self.w_anc.shape[0]
-        anchor = _bf16(B * La, n_anc, device=dev)
+        anchor = _h16(B * La, n_anc, device=dev, fmt=fmt)
         gemm(pooled, self.w_anc, self.b_anc, M=B * La, kpad=cpad, npad=n_anc, epi=EPI_QKV, n_store=n_anc, out_bf16=anchor,
              slot_scale=self.anc_scale)
         # attention
-        merged = _bf16(B * L, self.k_proj, device=dev, zero=self.k_proj != (hw + hs) * SLOT)
+        merged = _h16(B * L, self.k_proj, device=dev, fmt=fmt, zero=self.k_proj != (hw + hs) * SLOT)
         s = wa.shift_size
         gw = G.token_grid(x_size, wa.window_size, (s, s))
         attention(gw, gw, qkv, 0, qkv, hw * SLOT, qkv, 2 * hw * SLOT, merged, 0, B, hw, bias_w, t["mask_w"] is not None,
                   tag="window_attn")
         tok, anc = sa.grids(x_size)
         nW = (tok.H // tok.wh) * (tok.W // tok.ww)
-        x1 = _bf16(B * nW * hs * anc.wh * anc.ww, SLOT, device=dev)
+        x1 = _h16(B * nW * hs * anc.wh * anc.ww, SLOT, device=dev, fmt=fmt)
         use_mask = t["mask_a2w"] is not None
         attention(anc, tok, anchor, 0, qkv, (3 * hw + hs) * SLOT, qkv, (3 * hw + 2 * hs) * SLOT, x1, 0, B, hs, bias_1,
                   use_mask, o_dense=True, tag="stripe_attn")
@@ -253,40 +272,40 @@ class BlockPlan:
         # CAB
         cab_y = gate = None
         if self.cab:
-            t1 = _bf16(B, H, W, self.cmid_pad, device=dev)
+            t1 = _h16(B, H, W, self.cmid_pad, device=dev, fmt=fmt)
             conv3x3(x16.view(B, H, W, cpad), self.w_cab1, self.b_cab1, cpad, self.cmid_pad, n_store=self.cmid_pad,
                     act=K.ACT_GELU, out_bf16=t1)
-            cab_y = _bf16(B * L, cpad, device=dev)
+            cab_y = _h16(B * L, cpad, device=dev, fmt=fmt)
             conv3x3(t1, self.w_cab2, self.b_cab2, self.cmid_pad, cpad, n_store=cpad, out_bf16=cab_y)
             nbytes = lib.grl_tc_channel_gate_workspace(B, L, C)
             ws = torch.empty(max(nbytes, 4) // 4, device=dev, dtype=torch.float32)
             gate = torch.empty(B, C, device=dev, dtype=torch.float32)
             w1, b1, w2, b2 = self.ca
-            capi.check(lib.grl_tc_channel_gate(capi.ptr(cab_y), cpad, B, L, C, capi.ptr(w1), capi.ptr(b1), capi.ptr(w2),
+            capi.check(lib.grl_tc_channel_gate(capi.ptr(cab_y), cpad, fmt, B, L, C, capi.ptr(w1), capi.ptr(b1), capi.ptr(w2),
                                                capi.ptr(b2), w1.shape[0], capi.ptr(gate), capi.ptr(ws), nbytes,
                                                capi.stream()))
         # proj + LN1 + residual (+ CAB)
         y32 = torch.empty(B, L, C, device=dev, dtype=torch.float32)
-        y16 = _bf16(B, L, cpad, device=dev)
+        y16 = _h16(B, L, cpad, device=dev, fmt=fmt)
         gemm(merged, self.w_proj, self.b_proj, M=B * L, kpad=self.k_proj, npad=self.n_ln, epi=EPI_LN, n_store=self.n_ln,
              n_real=C, out_bf16=y16, out_f32=y32, res_f32=x32, C=C, gamma=blk.norm1.weight, beta=blk.norm1.bias,
              eps=blk.norm1.eps, res_scale=blk.res_scale, cab_y=cab_y, cab_gate=gate, L=L)
         # MLP + LN2 + residual
-        hid = _bf16(B * L, self.hpad, device=dev)
+        hid = _h16(B * L, self.hpad, device=dev, fmt=fmt)
         gemm(y16, self.w_fc1, self.b_fc1, M=B * L, kpad=cpad, npad=self.hpad, epi=EPI_BIAS_ACT, n_store=self.hpad,
              act=K.ACT_GELU, out_bf16=hid)
         z32 = torch.empty(B, L, C, device=dev, dtype=torch.float32)
-        z16 = _bf16(B, L, cpad, device=dev)
+        z16 = _h16(B, L, cpad, device=dev, fmt=fmt)
         gemm(hid, self.w_fc2, self.b_fc2, M=B * L, kpad=self.hpad, npad=self.n_ln, epi=EPI_LN, n_store=self.n_ln, n_real=C,
              out_bf16=z16, out_f32=z32, res_f32=y32, C=C, gamma=blk.norm2.weight, beta=blk.norm2.bias, eps=blk.norm2.eps,
              res_scale=blk.res_scale, L=L)
         return z32, z16
 
 
-def block_plan(blk):
+def block_plan(blk, fmt):
     plan = getattr(blk, "_tc_plan", None)
-    if plan is None or plan.key != _version_key(blk):
-        plan = BlockPlan(blk)
+    if plan is None or plan.key != (_version_key(blk), fmt):
+        plan = BlockPlan(blk, fmt)
         blk._tc_plan = plan
     return plan
 
@@ -294,18 +313,18 @@ def block_plan(blk):
 class ConvPlan:
     """One packed 3x3 conv (stage conv / head convs)."""
 
-    def __init__(self, conv, cin_pad):
-        self.key = _version_key(conv)
+    def __init__(self, conv, cin_pad, fmt):
+        self.key = (_version_key(conv), fmt)
         self.cout = conv.weight.shape[0]
         self.cin_pad = cin_pad
         self.npad = round_up(self.cout, 64)
-        self.w, self.b = pack_conv(conv, cin_pad, self.npad)
+        self.w, self.b = pack_conv(conv, cin_pad, self.npad, fmt)
 
 
-def conv_plan(owner, name, conv, cin_pad):
+def conv_plan(owner, name, conv, cin_pad, fmt):
     cache = owner.__dict__.setdefault("_tc_convs", {})
     plan = cache.get(name)
-    if plan is None or plan.key != _version_key(conv) or plan.cin_pad != cin_pad:
-        plan = ConvPlan(conv, cin_pad)
+    if plan is None or plan.key != (_version_key(conv), fmt) or plan.cin_pad != cin_pad:
+        plan = ConvPlan(conv, cin_pad, fmt)
         cache[name] = plan
     return plan

@@ -130,11 +130,14 @@ int grl_stripe_attn_f32(const float* qkv, int64_t ld_qkv, const float* anchor, i
 int grl_bias_table_scaled_f32(const float* table, int rows, const float* w1, const float* b1, const float* w2,
                               int hidden, int heads, float mul, float* out, void* stream);
 
-/* fp32 (M, C) rows of pitch ldx -> bf16 (M, Cpad) zero-padded; and back (bf16 rows of pitch ldx, column offset). */
-int grl_tc_pack_bf16(const float* x, int64_t ldx, void* y_bf16, int64_t M, int C, int Cpad, void* stream);
-int grl_tc_unpack_bf16(const void* x_bf16, int64_t ldx, int x_off, float* y, int64_t ldy, int64_t M, int C, void* stream);
-/* AvgPool2d(df) on bf16 channels-last data (AnchorLinear.pooling, mixed_attn_block.py:725). */
-int grl_tc_avgpool_bf16(const void* x_bf16, void* y_bf16, int B, int H, int W, int Cpad, int df, void* stream);
+/* `fmt` selects the 16-bit operand format everywhere below: 0 = fp16 (default: 11-bit mantissa, saturating
+ * converts; needed for the 0.01 dB PSNR gate), 1 = bf16.  Both run kind::f16 tcgen05.mma at the same rate. */
+
+/* fp32 (M, C) rows of pitch ldx -> 16-bit (M, Cpad) zero-padded; and back (16-bit rows of pitch ldx, column offset). */
+int grl_tc_pack16(const float* x, int64_t ldx, void* y16, int64_t M, int C, int Cpad, int fmt, void* stream);
+int grl_tc_unpack16(const void* x16, int64_t ldx, int x_off, float* y, int64_t ldy, int64_t M, int C, int fmt, void* stream);
+/* AvgPool2d(df) on 16-bit channels-last data (AnchorLinear.pooling, mixed_attn_block.py:725). */
+int grl_tc_avgpool16(const void* x16, void* y16, int B, int H, int W, int Cpad, int df, int fmt, void* stream);
 /* Per-slot multipliers of the packed qkv layout [win q|k|v][stripe q|k|v] x heads: exp(min(logit_scale, ln100))*log2(e)
  * on window q, stripe q (attn_transform2) and stripe k (attn_transform1); 1 on the other q/k slots; 0 on v slots
  * (mixed_attn_block_efficient.py:39). out: (3*hw + 3*hs) floats. */
@@ -142,7 +145,7 @@ int grl_tc_slot_scale(const float* ls_window, const float* ls_stripe1, const flo
                       float* out, void* stream);
 /* ChannelAttention gate from bf16 CAB features y (B, L, ld) (mixed_attn_block.py:948-967). */
 size_t grl_tc_channel_gate_workspace(int B, int64_t L, int C);
-int grl_tc_channel_gate(const void* y_bf16, int64_t ld, int B, int64_t L, int C, const float* w1, const float* b1,
+int grl_tc_channel_gate(const void* y16, int64_t ld, int fmt, int B, int64_t L, int C, const float* w1, const float* b1,
                         const float* w2, const float* b2, int R, float* gate, void* workspace, size_t workspace_bytes,
                         void* stream);
 
@@ -155,6 +158,7 @@ int grl_tc_channel_gate(const void* y_bf16, int64_t ld, int B, int64_t L, int C,
  *   epi 2  out = res_f32 + res_scale * LayerNorm(acc + b) (+ cab_y * cab_gate[token / L]) -> out_f32 + out_bf16
  *          MixedAttention.proj + norm1 + CAB add, Mlp.fc2 + norm2 (efficient.py:543-554); needs npad <= 256. */
 typedef struct {
+  int32_t fmt; /* 0 = fp16, 1 = bf16 */
   const void* x;
   const void* w;
   const float* bias;
@@ -187,6 +191,7 @@ int grl_tc_gemm(const GrlTcGemm* p, void* stream);
  * q/k/v: bf16 token rows (pitch ld*, element offset *_off of head 0's slot); v_dense/o_dense: the (B_, heads, N, 32)
  * intermediate X1 of the stripe attention; bias: (heads, rows) fp32 from grl_bias_table_scaled_f32(.., log2 e). */
 typedef struct {
+  int32_t fmt; /* 0 = fp16, 1 = bf16 */
   GrlGrid gq, gk;
   const void* q;
   int64_t ldq;

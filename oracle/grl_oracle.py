@@ -507,16 +507,35 @@ def param_shapes(cfg):
     return sh
 
 
-def synth_state_dict(cfg, seed=0):
+def synth_state_dict(cfg, seed=0, style="spread"):
     """Deterministic synthetic weights shared by reference, oracle and candidate:
-    one generator per parameter *name* (so the values do not depend on module construction order),
-    fan-in scaled weights, non-trivial biases / LayerNorm affine, and logit_scale spread over
-    [ln 5, ln 150] so the clamp at ln 100 is exercised."""
+    one generator per parameter *name* (so the values do not depend on module construction order).
+    style "spread" (default, used by every golden fixture): fan-in scaled weights, non-trivial biases / LayerNorm
+    affine, and logit_scale spread over [ln 5, ln 150] so the clamp at ln 100 is exercised -- a deliberately harsh,
+    near-chaotic network.  style "init": the distribution the reference's own constructor produces
+    (grl.py:455-462: Linear ~ trunc_normal(std 0.02) with zero bias, LayerNorm identity, logit_scale = ln 10,
+    Conv2d = PyTorch's default kaiming-uniform), i.e. what an untrained reference model computes."""
     import zlib
 
     sd = {}
     for name, shape in sorted(param_shapes(cfg).items()):
         g = torch.Generator().manual_seed((zlib.crc32(name.encode()) + 7919 * seed) % (2 ** 31))
+        if style == "init":
+            if name.endswith("logit_scale"):
+                v = torch.full(shape, log(10.0))
+            elif ".norm" in name or name.startswith("norm_"):
+                v = torch.ones(shape) if name.endswith("weight") else torch.zeros(shape)
+            elif len(shape) == 4 or (name.endswith("bias") and (name.startswith("conv") or ".conv." in name
+                                                                 or ".cab." in name or name.startswith("upsample"))):
+                fan_in = prod(param_shapes(cfg)[name.replace(".bias", ".weight")][1:])
+                bound = 1.0 / fan_in ** 0.5
+                v = (torch.rand(shape, generator=g) * 2 - 1) * bound
+            elif name.endswith("bias"):
+                v = torch.zeros(shape)
+            else:
+                v = torch.nn.init.trunc_normal_(torch.empty(shape), std=0.02, generator=g)
+            sd[name] = v.float()
+            continue
         if name.endswith("logit_scale"):
             v = log(5.0) + (log(150.0) - log(5.0)) * torch.rand(shape, generator=g)
         elif ".norm" in name or name.startswith("norm_"):

@@ -15,8 +15,9 @@ def rnd(shape, seed, scale=1.0):
     return torch.randn(shape, generator=torch.Generator().manual_seed(seed)) * scale
 
 
-def bf(t):
-    return t.to(torch.bfloat16).float()
+def bf(t, fmt=0):
+    """Round to the 16-bit operand format under test (0 = fp16, 1 = bf16)."""
+    return t.to(torch.bfloat16 if fmt else torch.float16).float()
 
 
 @pytest.fixture(scope="module")
@@ -28,19 +29,18 @@ def tc(pkg, device):
     return T
 
 
+@pytest.mark.parametrize("fmt", [0, 1])
 @pytest.mark.parametrize("M,K,N,act", [(128, 64, 64, 0), (1000, 180, 360, 1), (257, 192, 540, 0), (4096, 360, 180, 0),
                                        (130, 64, 30, 2)])
-def test_gemm_bias_act(tc, device, M, K, N, act):
-    from grl_image_restoration_b200 import functional as Kf
-
+def test_gemm_bias_act(tc, device, M, K, N, act, fmt):
     x, w, b = rnd((M, K), 1), rnd((N, K), 2, K ** -0.5), rnd((N,), 3)
     kpad, npad = tc.round_up(K, 64), tc.round_up(N, 64)
-    ref = F.linear(bf(x), bf(w), b)
+    ref = F.linear(bf(x, fmt), bf(w, fmt), b)
     ref = F.gelu(ref) if act == 1 else (F.leaky_relu(ref, 0.2) if act == 2 else ref)
-    x16 = tc.pack_rows(x.to(device), kpad)
-    w16 = tc._pad_matrix(w.to(device), npad, kpad)
+    x16 = tc.pack_rows(x.to(device), kpad, fmt)
+    w16 = tc._pad_matrix(w.to(device), npad, kpad, fmt=fmt)
     bp = tc._pad_vector(b.to(device), npad)
-    o16 = torch.empty(M, npad, device=device, dtype=torch.bfloat16)
+    o16 = torch.empty(M, npad, device=device, dtype=tc.DTYPE[fmt])
     o32 = torch.empty(M, N, device=device, dtype=torch.float32)
     tc.gemm(x16, w16, bp, M=M, kpad=kpad, npad=npad, n_store=npad, n_real=N, out_bf16=o16, out_f32=o32, act=act, slope=0.2)
     err = (o32.cpu() - ref).abs().max().item()
@@ -64,7 +64,7 @@ def test_conv3x3_tc(tc, device, B, H, W, Cin, Cout, act):
     wp, bp = tc.pack_conv(conv, cin_pad, npad)
     x16 = tc.pack_rows(x.permute(0, 2, 3, 1).contiguous().to(device), cin_pad)
     o32 = torch.empty(B, H, W, Cout, device=device, dtype=torch.float32)
-    o16 = torch.empty(B, H, W, npad, device=device, dtype=torch.bfloat16)
+    o16 = torch.empty(B, H, W, npad, device=device, dtype=torch.float16)
     tc.conv3x3(x16, wp, bp, cin_pad, npad, n_store=npad, n_real=Cout, act=act, slope=0.01, out_bf16=o16, out_f32=o32,
                res_f32=r.to(device))
     err = (o32.cpu() - ref).abs().max().item()
@@ -79,7 +79,7 @@ def test_gemm_qkv_epilogue(tc, device):
     rmap = [s * 32 + e for s in range(slots) for e in range(30)]
     w16 = tc._pad_matrix(w.to(device), slots * 32, 192, row_map=rmap)
     bp = tc._pad_vector(b.to(device), slots * 32, rmap)
-    out = torch.empty(M, slots * 32, device=device, dtype=torch.bfloat16)
+    out = torch.empty(M, slots * 32, device=device, dtype=torch.float16)
     tc.gemm(tc.pack_rows(x.to(device), 192), w16, bp, M=M, kpad=192, npad=slots * 32, epi=tc.EPI_QKV,
             n_store=slots * 32, out_bf16=out, slot_scale=scale.to(device))
     y = F.linear(bf(x), bf(w), b).view(M, slots, 30)
@@ -104,7 +104,7 @@ def test_gemm_layernorm_epilogue(tc, device, C, cab):
         ref = ref + bf(cy) * gate.repeat_interleave(L, 0)
         kw = dict(cab_y=cy16, cab_gate=gate.to(device))
     o32 = torch.empty(M, C, device=device, dtype=torch.float32)
-    o16 = torch.empty(M, cpad, device=device, dtype=torch.bfloat16)
+    o16 = torch.empty(M, cpad, device=device, dtype=torch.float16)
     tc.gemm(tc.pack_rows(x.to(device), K), tc._pad_matrix(w.to(device), n_ln, K), tc._pad_vector(b.to(device), n_ln), M=M,
             kpad=K, npad=n_ln, epi=tc.EPI_LN, n_store=n_ln, n_real=C, out_bf16=o16, out_f32=o32, res_f32=res.to(device),
             C=C, gamma=g.to(device), beta=be.to(device), eps=1e-5, res_scale=0.5, L=L, **kw)
@@ -114,14 +114,14 @@ def test_gemm_layernorm_epilogue(tc, device, C, cab):
         assert o16.cpu().float()[:, C:].abs().max().item() == 0
 
 
-def _attn_ref(q, k, v, bias_idx, table, mask):
+def _attn_ref(q, k, v, bias_idx, table, mask, fmt=0):
     """q (Bw, h, Nq, d) pre-normalised+scaled (log2 domain), k (Bw,h,Nk,d), v; table (h, rows) log2 domain."""
-    s = bf(q) @ bf(k).transpose(-1, -2)
+    s = bf(q, fmt) @ bf(k, fmt).transpose(-1, -2)
     s = s + table[:, bias_idx.reshape(-1)].view(table.shape[0], *bias_idx.shape).unsqueeze(0)
     if mask is not None:
         s = (s.view(-1, mask.shape[0], *s.shape[1:]) + (mask * 1.4426950408889634).unsqueeze(1).unsqueeze(0)).view(s.shape)
     p = torch.softmax(s * math.log(2.0), dim=-1)
-    return p @ bf(v)
+    return p @ bf(v, fmt)
 
 
 ATT = [  # B, H, W, (wh, ww), heads, shifted
@@ -130,8 +130,9 @@ ATT = [  # B, H, W, (wh, ww), heads, shifted
 ]
 
 
+@pytest.mark.parametrize("fmt", [0, 1])
 @pytest.mark.parametrize("B,H,W,ws,heads,shifted", ATT)
-def test_attention_tc_window(tc, oracle, device, B, H, W, ws, heads, shifted):
+def test_attention_tc_window(tc, oracle, device, B, H, W, ws, heads, shifted, fmt):
     from grl_image_restoration_b200 import geometry as G
 
     d, nsl = 30, 3 * heads
@@ -149,14 +150,14 @@ def test_attention_tc_window(tc, oracle, device, B, H, W, ws, heads, shifted):
         t = torch.roll(t, (-s, -s), (1, 2))
     win = oracle.partition(t, ws).reshape(-1, ws[0] * ws[1], 3, heads, 32).permute(2, 0, 3, 1, 4)
     mask = oracle.shift_mask([H, W], list(ws), [s, s]) if shifted else None
-    o = _attn_ref(win[0], win[1], win[2], oracle.position_index(list(ws)), table, mask)
+    o = _attn_ref(win[0], win[1], win[2], oracle.position_index(list(ws)), table, mask, fmt)
     o = o.transpose(1, 2).reshape(-1, ws[0], ws[1], heads * 32)
     ref = oracle.unpartition(o, ws, (H, W))
     if s:
         ref = torch.roll(ref, (s, s), (1, 2))
     ref = ref.reshape(B, L, heads * 32)
-    q16 = qkv.view(B * L, nsl * 32).to(device).to(torch.bfloat16)
-    out = torch.zeros(B * L, heads * 32, device=device, dtype=torch.bfloat16)
+    q16 = qkv.view(B * L, nsl * 32).to(device).to(tc.DTYPE[fmt])
+    out = torch.zeros(B * L, heads * 32, device=device, dtype=tc.DTYPE[fmt])
     grid = G.token_grid((H, W), ws, (s, s))
     tc.attention(grid, grid, q16, 0, q16, heads * 32, q16, 2 * heads * 32, out, 0, B, heads, table.to(device), shifted)
     got = out.cpu().float().view(B, L, heads * 32)
@@ -201,12 +202,12 @@ def test_attention_tc_stripe_chain(tc, oracle, device, B, H, W, stripe, df, head
     if shifted:
         ref = torch.roll(ref, (sh[0], sh[1]), (1, 2))
     ref = ref.reshape(B, L, heads * 32)
-    q16 = qkv.view(B * L, -1).to(device).to(torch.bfloat16)
-    a16 = anc.view(B * Ha * Wa, -1).to(device).to(torch.bfloat16)
+    q16 = qkv.view(B * L, -1).to(device).to(torch.float16)
+    a16 = anc.view(B * Ha * Wa, -1).to(device).to(torch.float16)
     tok, ag = G.token_grid((H, W), ss, sh), G.anchor_grid((H, W), ss, sh, df)
     nW = (H // ss[0]) * (W // ss[1])
-    x1d = torch.empty(B * nW * heads * ass[0] * ass[1], 32, device=device, dtype=torch.bfloat16)
-    out = torch.zeros(B * L, heads * 32, device=device, dtype=torch.bfloat16)
+    x1d = torch.empty(B * nW * heads * ass[0] * ass[1], 32, device=device, dtype=torch.float16)
+    out = torch.zeros(B * L, heads * 32, device=device, dtype=torch.float16)
     tc.attention(ag, tok, a16, 0, q16, heads * 32, q16, 2 * heads * 32, x1d, 0, B, heads, t1.to(device), shifted, o_dense=True)
     tc.attention(tok, ag, q16, 0, a16, 0, x1d, 0, out, 0, B, heads, t2.to(device), shifted, v_dense=True)
     got = out.cpu().float().view(B, L, heads * 32)

@@ -18,13 +18,14 @@ ap.add_argument("--size", type=int, default=256)
 ap.add_argument("--batch", type=int, default=1)
 ap.add_argument("--iters", type=int, default=3)
 ap.add_argument("--precision", default=None)
+ap.add_argument("--style", default="spread")
 a = ap.parse_args()
 pkg = load_package()
 import grl_oracle as orc  # noqa: E402  (weights only)
 
 cfg = pkg.configs.grl_config(a.variant, a.task, a.scale, a.size)
 m = pkg.GRL(**cfg)
-m.load_state_dict(orc.synth_state_dict(cfg, 0), strict=False)
+m.load_state_dict(orc.synth_state_dict(cfg, 0, a.style), strict=False)
 m = m.cuda().eval()
 if a.precision is not None and hasattr(m, "set_precision"):
     m.set_precision(a.precision)
