@@ -40,7 +40,7 @@ class GrlTcAttn(ctypes.Structure):
                 ("ldk", c_i64), ("k_off", ctypes.c_int32), ("v", c_vp), ("ldv", c_i64), ("v_off", ctypes.c_int32),
                 ("v_dense", ctypes.c_int32), ("out", c_vp), ("ldo", c_i64), ("o_off", ctypes.c_int32),
                 ("o_dense", ctypes.c_int32), ("B", ctypes.c_int32), ("heads", ctypes.c_int32), ("bias", c_vp),
-                ("rows", ctypes.c_int32), ("use_mask", ctypes.c_int32)]
+                ("rows", ctypes.c_int32), ("rows_pad", ctypes.c_int32), ("use_mask", ctypes.c_int32)]
 
 
 _SIGNATURES = {
@@ -52,7 +52,7 @@ _SIGNATURES = {
     "grl_shift_mask_host": (c_int, [c_int] * 8 + [c_vp]),
     "grl_coords_table_host": (c_int, [c_int, c_int, c_int, c_vp]),
     "grl_bias_table_f32": (c_int, [c_vp, c_int, c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_vp]),
-    "grl_bias_table_scaled_f32": (c_int, [c_vp, c_int, c_vp, c_vp, c_vp, c_int, c_int, c_f32, c_vp, c_vp]),
+    "grl_tc_bias_table4": (c_int, [c_vp, c_int, c_vp, c_vp, c_vp, c_int, c_int, c_f32, c_int, c_vp, c_vp]),
     "grl_tc_pack16": (c_int, [c_vp, c_i64, c_vp, c_i64, c_int, c_int, c_int, c_vp]),
     "grl_tc_unpack16": (c_int, [c_vp, c_i64, c_int, c_vp, c_i64, c_i64, c_int, c_int, c_vp]),
     "grl_tc_avgpool16": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp]),

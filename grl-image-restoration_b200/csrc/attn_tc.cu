@@ -15,6 +15,8 @@
 //   Oj = P V          A = P,  B = V tile [KT keys x 32] MN-major SW64                        -> TMEM cols [KT, KT+32)
 // The running output lives in registers (o = o * corr + Oj), so TMEM is never read-modify-written.
 // Several CTAs are co-resident per SM (3 at KT = 64), which is what overlaps one CTA's MMAs with another's softmax.
+#include <stdlib.h>
+
 #include "grl_common.cuh"
 #include "ops_f32.h"
 #include "ops_tc.h"
@@ -43,16 +45,27 @@ struct AttnSmem {
   static constexpr int P_BYTES = kQT * KT * 2;
   static constexpr int OFF_K = Q_BYTES;
   static constexpr int OFF_V = OFF_K + 2 * KV_BYTES;
-  static constexpr int OFF_P = OFF_V + 2 * KV_BYTES;
-  static constexpr int OFF_META = OFF_P + P_BYTES;           // int koff[2][KT], rid[2][KT]
-  static constexpr int OFF_BAR = OFF_META + 4 * KT * 4;
-  static constexpr int TOTAL = OFF_BAR + 64 + 1024;
-  static_assert(OFF_P % 1024 == 0, "P tile must be 1024-byte aligned for SWIZZLE_128B");
+  static constexpr int OFF_P = (OFF_V + 2 * KV_BYTES + 1023) / 1024 * 1024;  // two P buffers
+  static constexpr int OFF_META = OFF_P + 2 * P_BYTES;                       // int koff[3][KT], rid[3][KT] (tile % 3)
+  static constexpr int OFF_BAR = OFF_META + 6 * KT * 4;
+  static constexpr int TOTAL = OFF_BAR + 128 + 1024;
+  static_assert(P_BYTES % 1024 == 0, "P tiles must be 1024-byte aligned for SWIZZLE_128B");
 };
 
-// KW: key-window width when it is a power of two that tiles KT (bias addressing with immediates), 0 = generic
+constexpr int kAttnThreads = kQT + 32;  // 4 softmax warps (one query row per thread) + 1 producer / MMA warp
+
+// Warp-specialised pipeline without block-wide barriers in the loop (tiles t = 0..nt-1 of KT keys):
+//   warp 4 (producer + MMA issuer): cp.async gathers of Q / K_t / V_t (roll + partition addressing), then
+//       QK(t+1) as soon as every softmax thread has pulled S_t out of TMEM (s_free), PV(t) as soon as P_t is in smem
+//       and O_{t-1} has been consumed (p_full); completion is signalled by tcgen05.commit on bar_s / bar_o.
+//   warps 0-3 (softmax, thread = query row = TMEM lane): wait bar_s(t) -> S_t + bias -> registers -> arrive s_free ->
+//       exp2 / running max / bf16|fp16 P_t -> smem -> wait bar_o(t-1), o = (o + O_{t-1}) * corr_t -> arrive p_full.
+// The only waits of a softmax warp are on MMA completions.
+// KW: key-window width when it is a power of two >= 8 (bias rows read as aligned float4 from the 4-way shifted table
+// copies), 0 = generic scalar path.
 template <int KT, int KW>
-__global__ void __launch_bounds__(kQT, 3) attn_tc_kernel(const AttnTcArgs a) {
+__global__ void __launch_bounds__(kAttnThreads, 3) attn_tc_kernel(const AttnTcArgs a) {
+  static_assert(KT == 64 || KT == 128, "P tiles are 128-byte rows (64 keys) with SWIZZLE_128B");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   using S = AttnSmem<KT>;
@@ -60,13 +73,16 @@ __global__ void __launch_bounds__(kQT, 3) attn_tc_kernel(const AttnTcArgs a) {
   uint8_t* Ks = smem + S::OFF_K;
   uint8_t* Vs = smem + S::OFF_V;
   uint8_t* Ps = smem + S::OFF_P;
-  int* koff_s = reinterpret_cast<int*>(smem + S::OFF_META);  // [2][KT]
-  int* krid_s = koff_s + 2 * KT;                              // [2][KT]
-  uint64_t* bar_s = reinterpret_cast<uint64_t*>(smem + S::OFF_BAR);
-  uint64_t* bar_o = bar_s + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_o + 1);
+  int* koff_s = reinterpret_cast<int*>(smem + S::OFF_META);  // [3][KT]
+  int* krid_s = koff_s + 3 * KT;                              // [3][KT]
+  uint64_t* bar_s = reinterpret_cast<uint64_t*>(smem + S::OFF_BAR);  // QK(t) complete          (tcgen05.commit)
+  uint64_t* bar_o = bar_s + 1;                                        // PV(t) complete          (tcgen05.commit)
+  uint64_t* s_free = bar_s + 2;                                       // S_t read by all rows    (128 arrivals)
+  uint64_t* p_full = bar_s + 3;                                       // P_t written, O_{t-1} consumed (128 arrivals)
+  uint64_t* meta_full = bar_s + 4;                                    // [3] koff / rid of tile t (32 arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_s + 8);
 
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int Nq = a.gq.wh * a.gq.ww, Nk = a.gk.wh * a.gk.ww;
   const int nqt = (Nq + kQT - 1) / kQT;
   const int nww = a.gq.W / a.gq.ww;
@@ -81,188 +97,266 @@ __global__ void __launch_bounds__(kQT, 3) attn_tc_kernel(const AttnTcArgs a) {
   const int wr = w / nww, wc = w - wr * nww;
   const int Wt = a.gq.ww + a.gk.ww - 1;
   const int ntiles = (Nk + KT - 1) / KT;
-  constexpr uint32_t TMEM_COLS = (KT + kDP <= 128) ? 128 : 256;
+  constexpr uint32_t TMEM_COLS = (KT + kDP <= 64) ? 64 : 128;
+  static_assert(KT + kDP <= 128, "S + O must fit 128 TMEM columns");
 
   if (tid == 0) {
     mbar_init(bar_s, 1);
     mbar_init(bar_o, 1);
+    mbar_init(s_free, kQT);
+    mbar_init(p_full, kQT);
+    for (int i = 0; i < 3; ++i) mbar_init(&meta_full[i], 32);
     mbar_init_fence();
   }
-  if (warp == 0) tmem_alloc(tmem_slot, TMEM_COLS);
-
-  // ---- this thread's query row
-  const int qi = qt * kQT + tid;
-  const bool q_ok = qi < Nq;
-  const Tok tq = locate(a.gq, wr, wc, q_ok ? qi : 0);
-  const long long q_tok = (long long)(b * a.gq.H + tq.y) * a.gq.W + tq.x;
-  {
-    const __nv_bfloat16* src = a.q + q_tok * a.ldq + a.q_off + h * kDP;
-#pragma unroll
-    for (int c = 0; c < 4; ++c) cp_async_16(Qs + sw64(tid, c), src + c * 8, q_ok);
-  }
-  // ---- K / V tile loader: thread t < KT gathers key row t of the tile (K and V)
-  auto load_tile = [&](int tile, int buf) {
-    const int k0 = tile * KT;
-    for (int r = tid; r < KT; r += kQT) {
-      const int kj = k0 + r;
-      const bool ok = kj < Nk;
-      const Tok tk = locate(a.gk, wr, wc, ok ? kj : 0);
-      const long long tok = (long long)(b * a.gk.H + tk.y) * a.gk.W + tk.x;
-      const __nv_bfloat16* ksrc = a.k + tok * a.ldk + a.k_off + h * kDP;
-      const __nv_bfloat16* vsrc = a.v_dense ? a.v + (((long long)bw * a.heads + h) * Nk + (ok ? kj : 0)) * kDP
-                                            : a.v + tok * a.ldv + a.v_off + h * kDP;
-      uint8_t* kd = Ks + buf * S::KV_BYTES;
-      uint8_t* vd = Vs + buf * S::KV_BYTES;
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        cp_async_16(kd + sw64(r, c), ksrc + c * 8, ok);
-        cp_async_16(vd + sw64(r, c), vsrc + c * 8, ok);
-      }
-      koff_s[buf * KT + r] = tk.ih * Wt + tk.iw;
-      krid_s[buf * KT + r] = region_id(a.gk, tk.r, tk.c);
-    }
-  };
-  load_tile(0, 0);
-  cp_async_commit();
-  if (ntiles > 1) load_tile(1, 1);
-  cp_async_commit();
-
+  if (warp == 4) tmem_alloc(tmem_slot, TMEM_COLS);
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
-
-  // bias row base for this query:  idx(i, j) = base_i - koff_j   (grl_geometry.h rel_index)
-  const float* bias_h = a.bias + (size_t)h * a.rows;
-  const int base_i = (tq.ih + a.gk.wh - 1) * Wt + tq.iw + a.gk.ww - 1;
-  const int q_rid = region_id(a.gq, tq.r, tq.c);
-  const bool need_mask = a.use_mask && (wr == nwh - 1 || wc == nww - 1);
-
-  float o[kDP];
-#pragma unroll
-  for (int e = 0; e < kDP; ++e) o[e] = 0.f;
-  float m_run = -INFINITY, l_run = 0.f;
-
-  const uint32_t idesc_qk = umma_idesc(kQT, KT, a.fmt, 0, 0);
-  const uint32_t idesc_pv = umma_idesc(kQT, kDP, a.fmt, 0, 1);
   const int fmt = a.fmt;
-  const uint32_t q_sa = smem_u32(Qs), p_sa = smem_u32(Ps);
 
-  for (int t = 0; t < ntiles; ++t) {
-    const int buf = t & 1;
-    const int k0 = t * KT;
-    if (t + 1 < ntiles) cp_async_wait<1>(); else cp_async_wait<0>();
-    fence_proxy_async_smem();
-    __syncthreads();
-    if (tid == 0) {
-      tcgen05_fence_after();
-      const uint32_t k_sa = smem_u32(Ks + buf * S::KV_BYTES);
+  if (warp == 4) {
+    // =============================================================== producer + MMA issuer
+    auto load_q = [&]() {
+      for (int r = lane; r < kQT; r += 32) {
+        const int qi = qt * kQT + r;
+        const bool ok = qi < Nq;
+        const Tok tq = locate(a.gq, wr, wc, ok ? qi : 0);
+        const __nv_bfloat16* src = a.q + ((long long)(b * a.gq.H + tq.y) * a.gq.W + tq.x) * a.ldq + a.q_off + h * kDP;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) cp_async_16(Qs + sw64(r, c), src + c * 8, ok);
+      }
+    };
+    auto load_k = [&](int tile) {
+      const int buf = tile & 1, k0 = tile * KT, slot = tile % 3;
+      for (int r = lane; r < KT; r += 32) {
+        const int kj = k0 + r;
+        const bool ok = kj < Nk;
+        const Tok tk = locate(a.gk, wr, wc, ok ? kj : 0);
+        const __nv_bfloat16* ksrc = a.k + ((long long)(b * a.gk.H + tk.y) * a.gk.W + tk.x) * a.ldk + a.k_off + h * kDP;
+        uint8_t* kd = Ks + buf * S::KV_BYTES;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) cp_async_16(kd + sw64(r, c), ksrc + c * 8, ok);
+        koff_s[slot * KT + r] = tk.ih * Wt + tk.iw;
+        krid_s[slot * KT + r] = region_id(a.gk, tk.r, tk.c);
+      }
+      mbar_arrive(&meta_full[slot]);  // release: koff / rid of this tile are published
+    };
+    auto load_v = [&](int tile) {
+      const int buf = tile & 1, k0 = tile * KT;
+      for (int r = lane; r < KT; r += 32) {
+        const int kj = k0 + r;
+        const bool ok = kj < Nk;
+        const __nv_bfloat16* vsrc;
+        if (a.v_dense) {
+          vsrc = a.v + (((long long)bw * a.heads + h) * Nk + (ok ? kj : 0)) * kDP;
+        } else {
+          const Tok tk = locate(a.gk, wr, wc, ok ? kj : 0);
+          vsrc = a.v + ((long long)(b * a.gk.H + tk.y) * a.gk.W + tk.x) * a.ldv + a.v_off + h * kDP;
+        }
+        uint8_t* vd = Vs + buf * S::KV_BYTES;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) cp_async_16(vd + sw64(r, c), vsrc + c * 8, ok);
+      }
+    };
+    const uint32_t idesc_qk = umma_idesc(kQT, KT, fmt, 0, 0);
+    const uint32_t idesc_pv = umma_idesc(kQT, kDP, fmt, 0, 1);
+    const uint32_t q_sa = smem_u32(Qs), p_sa = smem_u32(Ps);
+    auto issue_qk = [&](int tile) {  // lane 0 only
+      const uint32_t k_sa = smem_u32(Ks + (tile & 1) * S::KV_BYTES);
 #pragma unroll
       for (int k = 0; k < kDP / 16; ++k)
-        umma_ss(tmem, umma_desc(q_sa + k * 32, 16, 512, SWZ_64B), umma_desc(k_sa + k * 32, 16, 512, SWZ_64B), idesc_qk,
-                k != 0);
+        umma_ss(tmem, umma_desc(q_sa + k * 32, 16, 512, SWZ_64B), umma_desc(k_sa + k * 32, 16, 512, SWZ_64B), idesc_qk, k != 0);
       umma_commit(bar_s);
-    }
-    mbar_wait(bar_s, t & 1);
-    tcgen05_fence_after();
+    };
+    // all of this warp's outstanding gathers have landed and are visible to the tensor core (async proxy)
+    auto publish_loads = [&]() {
+      cp_async_wait<0>();
+      fence_proxy_async_smem();
+      __syncwarp();
+    };
 
-    // ---- logits of this tile (log2 domain), row max
-    float lg[KT];
-    float m_tile = -INFINITY;
-#pragma unroll
-    for (int c0 = 0; c0 < KT; c0 += 32) {
-      uint32_t v[32];
-      tmem_ld32(trow + c0, v);
-      tmem_ld_wait();
-      if (KW > 0 && k0 + KT <= Nk) {  // full tile: immediate-offset runs (tail tiles take the clamped generic path)
-        constexpr int KWS = KW > 0 ? KW : 1;  // (KW == 0 never reaches this branch)
-        constexpr int RW = (KWS >= 32) ? 32 : KWS;  // run length of consecutive keys in one key row inside this chunk
-#pragma unroll
-        for (int r0 = 0; r0 < 32; r0 += RW) {
-          const int kj = k0 + c0 + r0;  // first key of the run (CTA-uniform)
-          const float* bp = bias_h + base_i - ((kj / KWS) * Wt + (kj % KWS));
-#pragma unroll
-          for (int j = 0; j < RW; ++j) lg[c0 + r0 + j] = __uint_as_float(v[r0 + j]) + __ldg(bp - j);
-        }
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          lg[c0 + j] = __uint_as_float(v[j]) + __ldg(bias_h + base_i - koff_s[buf * KT + c0 + j]);
-      }
-    }
-    if (need_mask) {
-#pragma unroll
-      for (int j = 0; j < KT; ++j)
-        if (krid_s[buf * KT + j] != q_rid) lg[j] += kMaskLog2;
-    }
-    if (k0 + KT > Nk) {
-#pragma unroll
-      for (int j = 0; j < KT; ++j)
-        if (k0 + j >= Nk) lg[j] = -INFINITY;
-    }
-#pragma unroll
-    for (int j = 0; j < KT; ++j) m_tile = fmaxf(m_tile, lg[j]);
-    const float m_new = fmaxf(m_run, m_tile);
-    const float corr = ex2(m_run - m_new);
-    m_run = m_new;
-    float psum = 0.f;
-#pragma unroll
-    for (int c = 0; c < KT / 8; ++c) {
-      float p[8];
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        p[e] = ex2(lg[c * 8 + e] - m_new);
-        psum += p[e];
-      }
-      const uint4 pk = make_uint4(pack16(p[0], p[1], fmt), pack16(p[2], p[3], fmt), pack16(p[4], p[5], fmt), pack16(p[6], p[7], fmt));
-      // [128 x KT] K-major SWIZZLE_128B, 64-key sub-tiles of 16 KB
-      const int sub = c >> 3, cc = c & 7;
-      *reinterpret_cast<uint4*>(Ps + sub * (kQT * 128) + tid * 128 + ((cc ^ (tid & 7)) << 4)) = pk;
-    }
-    l_run = l_run * corr + psum;
-
-    tcgen05_fence_before();
-    fence_proxy_async_smem();
-    __syncthreads();
-    if (tid == 0) {
+    load_q();
+    load_k(0);
+    if (ntiles > 1) load_k(1);
+    load_v(0);
+    cp_async_commit();
+    publish_loads();
+    if (lane == 0) {
       tcgen05_fence_after();
-      const uint32_t v_sa = smem_u32(Vs + buf * S::KV_BYTES);
-#pragma unroll
-      for (int k = 0; k < KT / 16; ++k) {
-        const uint32_t pa = p_sa + (k >> 2) * (kQT * 128) + (k & 3) * 32;
-        umma_ss(tmem + KT, umma_desc(pa, 16, 1024, SWZ_128B), umma_desc(v_sa + k * 1024, 16, 512, SWZ_64B), idesc_pv,
-                k != 0);
-      }
-      umma_commit(bar_o);
+      issue_qk(0);
     }
-    mbar_wait(bar_o, t & 1);
-    tcgen05_fence_after();
+    for (int t = 0; t < ntiles; ++t) {
+      // ---- QK(t+1): K_{t+1} was requested an iteration ago; the S columns are free once every row has read S_t
+      if (t + 1 < ntiles) {
+        publish_loads();
+        mbar_wait(s_free, t & 1);
+        if (lane == 0) {
+          tcgen05_fence_after();
+          issue_qk(t + 1);
+        }
+      }
+      // K buffer t&1 is free (QK(t) completed before anyone could read S_t)
+      if (t + 2 < ntiles) load_k(t + 2);
+      cp_async_commit();
+      // ---- PV(t): V_t landed; P_t written and O_{t-1} consumed by every row
+      publish_loads();
+      mbar_wait(p_full, t & 1);
+      if (lane == 0) {
+        tcgen05_fence_after();
+        const uint32_t v_sa = smem_u32(Vs + (t & 1) * S::KV_BYTES);
+        const uint32_t pt_sa = p_sa + (t & 1) * S::P_BYTES;
+#pragma unroll
+        for (int k = 0; k < KT / 16; ++k) {
+          const uint32_t pa = pt_sa + (k >> 2) * (kQT * 128) + (k & 3) * 32;
+          umma_ss(tmem + KT, umma_desc(pa, 16, 1024, SWZ_128B), umma_desc(v_sa + k * 1024, 16, 512, SWZ_64B), idesc_pv, k != 0);
+        }
+        umma_commit(bar_o);
+      }
+      // V buffer (t+1)&1 held V_{t-1}.  PV(t-1) is complete: every row waited for it before arriving on p_full(t).
+      // (Waiting on bar_o here would be wrong as well as redundant: PV(t) may already have flipped the barrier
+      // again, and a parity wait on the older phase would then sleep until a phase that needs this warp.)
+      if (t + 1 < ntiles) load_v(t + 1);
+      cp_async_commit();
+    }
+    mbar_wait(bar_o, (ntiles - 1) & 1);  // keep TMEM alive until the last MMA is done
+  } else {
+    // =============================================================== softmax warps: thread = query row
+    const int qi = qt * kQT + tid;
+    const bool q_ok = qi < Nq;
+    const Tok tq = locate(a.gq, wr, wc, q_ok ? qi : 0);
+    const long long q_tok = (long long)(b * a.gq.H + tq.y) * a.gq.W + tq.x;
+    const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+    // bias:  idx(i, j) = base_i - koff_j  (grl_geometry.h rel_index); table copy c holds T shifted right by c entries
+    const float* bias_h = a.bias + (size_t)h * 4 * a.rows_pad;
+    const int base_i = (tq.ih + a.gk.wh - 1) * Wt + tq.iw + a.gk.ww - 1;
+    const int q_rid = region_id(a.gq, tq.r, tq.c);
+    const bool need_mask = a.use_mask && (wr == nwh - 1 || wc == nww - 1);
+
+    float o[kDP];
+#pragma unroll
+    for (int e = 0; e < kDP; ++e) o[e] = 0.f;
+    float m_run = -INFINITY, l_run = 0.f;
+
+    for (int t = 0; t < ntiles; ++t) {
+      const int buf = t & 1, k0 = t * KT, slot = t % 3;
+      mbar_wait(bar_s, t & 1);
+      tcgen05_fence_after();
+      const bool full_tile = (KW > 0) && (k0 + KT <= Nk);
+      if (!full_tile || need_mask) mbar_wait(&meta_full[slot], (t / 3) & 1);
+
+      // ---- logits of this tile (log2 domain): S from TMEM + bias
+      float lg[KT];
+#pragma unroll
+      for (int c0 = 0; c0 < KT; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(trow + c0, v);
+        tmem_ld_wait();
+        if (full_tile) {
+          constexpr int KWS = KW > 0 ? KW : 4;
+          constexpr int RW = (KWS >= 32) ? 32 : KWS;  // consecutive keys of one key row inside this chunk
+#pragma unroll
+          for (int r0 = 0; r0 < 32; r0 += RW) {
+            const int kj = k0 + c0 + r0;  // first key of the run (CTA-uniform, multiple of 4)
+            const int s0 = base_i - ((kj / KWS) * Wt + (kj % KWS)) - 3;  // table index of key kj + 3
+            const int cpy = (-s0) & 3;
+            const float4* bp = reinterpret_cast<const float4*>(bias_h + (size_t)cpy * a.rows_pad + (s0 + cpy));
+#pragma unroll
+            for (int qd = 0; qd < RW / 4; ++qd) {
+              const float4 bb = __ldg(bp - qd);
+              const int j = c0 + r0 + 4 * qd;
+              lg[j + 0] = __uint_as_float(v[r0 + 4 * qd + 0]) + bb.w;
+              lg[j + 1] = __uint_as_float(v[r0 + 4 * qd + 1]) + bb.z;
+              lg[j + 2] = __uint_as_float(v[r0 + 4 * qd + 2]) + bb.y;
+              lg[j + 3] = __uint_as_float(v[r0 + 4 * qd + 3]) + bb.x;
+            }
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            lg[c0 + j] = __uint_as_float(v[j]) + __ldg(bias_h + base_i - koff_s[slot * KT + c0 + j]);
+        }
+      }
+      tcgen05_fence_before();
+      mbar_arrive(s_free);  // this row no longer needs S_t in TMEM
+
+      if (need_mask) {
+#pragma unroll
+        for (int j = 0; j < KT; ++j)
+          if (krid_s[slot * KT + j] != q_rid) lg[j] += kMaskLog2;
+      }
+      if (k0 + KT > Nk) {
+#pragma unroll
+        for (int j = 0; j < KT; ++j)
+          if (k0 + j >= Nk) lg[j] = -INFINITY;
+      }
+      float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+      for (int j = 0; j < KT; j += 4) {
+        mx[0] = fmaxf(mx[0], lg[j]), mx[1] = fmaxf(mx[1], lg[j + 1]);
+        mx[2] = fmaxf(mx[2], lg[j + 2]), mx[3] = fmaxf(mx[3], lg[j + 3]);
+      }
+      const float m_new = fmaxf(fmaxf(m_run, fmaxf(mx[0], mx[1])), fmaxf(mx[2], mx[3]));
+      const float corr = ex2(m_run - m_new);
+      m_run = m_new;
+      float ps[4] = {0.f, 0.f, 0.f, 0.f};  // independent partial sums (no 64-long dependent FADD chain)
+      uint8_t* Pt = Ps + buf * S::P_BYTES;
+#pragma unroll
+      for (int c = 0; c < KT / 8; ++c) {
+        float p[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          p[e] = ex2(lg[c * 8 + e] - m_new);
+          ps[e & 3] += p[e];
+        }
+        uint4 pk;
+        if (fmt == FMT_BF16)
+          pk = make_uint4(pack_bf16(p[0], p[1]), pack_bf16(p[2], p[3]), pack_bf16(p[4], p[5]), pack_bf16(p[6], p[7]));
+        else
+          pk = make_uint4(pack_f16(p[0], p[1]), pack_f16(p[2], p[3]), pack_f16(p[4], p[5]), pack_f16(p[6], p[7]));
+        // [128 x KT] K-major SWIZZLE_128B, 64-key sub-tiles of 16 KB
+        const int sub = c >> 3, cc = c & 7;
+        *reinterpret_cast<uint4*>(Pt + sub * (kQT * 128) + tid * 128 + ((cc ^ (tid & 7)) << 4)) = pk;
+      }
+      l_run = l_run * corr + ((ps[0] + ps[1]) + (ps[2] + ps[3]));
+
+      // ---- fold in the previous tile's P V (it has had a whole softmax to finish) and rescale
+      if (t > 0) {
+        mbar_wait(bar_o, (t - 1) & 1);
+        tcgen05_fence_after();
+        uint32_t v[32];
+        tmem_ld32(trow + KT, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < kDP; ++e) o[e] = (o[e] + __uint_as_float(v[e])) * corr;
+      }
+      tcgen05_fence_before();
+      fence_proxy_async_smem();  // P_t (generic-proxy stores) -> visible to the tensor core
+      mbar_arrive(p_full);
+    }
     {
+      mbar_wait(bar_o, (ntiles - 1) & 1);
+      tcgen05_fence_after();
       uint32_t v[32];
       tmem_ld32(trow + KT, v);
       tmem_ld_wait();
 #pragma unroll
-      for (int e = 0; e < kDP; ++e) o[e] = fmaf(o[e], corr, __uint_as_float(v[e]));
+      for (int e = 0; e < kDP; ++e) o[e] += __uint_as_float(v[e]);
+    }
+    if (q_ok) {
+      const float inv = 1.0f / l_run;
+      __nv_bfloat16* dst = a.o_dense ? a.out + (((long long)bw * a.heads + h) * Nq + qi) * kDP
+                                     : a.out + q_tok * a.ldo + a.o_off + h * kDP;
+#pragma unroll
+      for (int e = 0; e < kDP; e += 8)
+        *reinterpret_cast<uint4*>(dst + e) =
+            make_uint4(pack16(o[e] * inv, o[e + 1] * inv, fmt), pack16(o[e + 2] * inv, o[e + 3] * inv, fmt),
+                       pack16(o[e + 4] * inv, o[e + 5] * inv, fmt), pack16(o[e + 6] * inv, o[e + 7] * inv, fmt));
     }
     tcgen05_fence_before();
-    __syncthreads();  // buffers `buf`, P and the TMEM columns are free again
-    if (t + 2 < ntiles) load_tile(t + 2, buf);
-    cp_async_commit();
-  }
-
-  if (q_ok) {
-    const float inv = 1.0f / l_run;
-    __nv_bfloat16* dst = a.o_dense ? a.out + (((long long)bw * a.heads + h) * Nq + qi) * kDP
-                                   : a.out + q_tok * a.ldo + a.o_off + h * kDP;
-#pragma unroll
-    for (int e = 0; e < kDP; e += 8)
-      *reinterpret_cast<uint4*>(dst + e) =
-          make_uint4(pack16(o[e] * inv, o[e + 1] * inv, fmt), pack16(o[e + 2] * inv, o[e + 3] * inv, fmt),
-                     pack16(o[e + 4] * inv, o[e + 5] * inv, fmt), pack16(o[e + 6] * inv, o[e + 7] * inv, fmt));
   }
   __syncthreads();
-  if (warp == 0) {
+  if (warp == 4) {
     tcgen05_fence_after();
     tmem_dealloc(tmem, TMEM_COLS);
   }
@@ -276,7 +370,7 @@ static int launch_attn_one(const AttnTcArgs& a, unsigned nblk, cudaStream_t st) 
     GRL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnSmem<KT>::TOTAL));
     configured = true;
   }
-  kern<<<nblk, kQT, AttnSmem<KT>::TOTAL, st>>>(a);
+  kern<<<nblk, kAttnThreads, AttnSmem<KT>::TOTAL, st>>>(a);
   GRL_LAUNCH_CHECK("attn_tc_kernel");
   return GRL_OK;
 }
@@ -289,17 +383,18 @@ int launch_attn_tc(const AttnTcArgs& a, cudaStream_t st) {
   GRL_REQUIRE(a.gq.H / a.gq.wh == a.gk.H / a.gk.wh && a.gq.W / a.gq.ww == a.gk.W / a.gk.ww,
               "attn_tc: query and key grids have different window counts");
   GRL_REQUIRE(a.heads >= 1 && a.heads <= 8, "attn_tc: heads=%d unsupported", a.heads);
+  GRL_REQUIRE(a.rows_pad % 4 == 0 && a.rows_pad >= a.rows + 4, "attn_tc: bias table pitch %d too small for %d rows", a.rows_pad,
+              a.rows);
   const int Nq = a.gq.wh * a.gq.ww;
   const long long nblk = (long long)a.B * (a.gq.H / a.gq.wh) * (a.gq.W / a.gq.ww) * a.heads * ceil_div(Nq, kQT);
   GRL_REQUIRE(nblk < (1ll << 31), "attn_tc: grid too large");
-  constexpr int KT = 64;
   switch (a.gk.ww) {
-    case 8: return launch_attn_one<KT, 8>(a, (unsigned)nblk, st);
-    case 16: return launch_attn_one<KT, 16>(a, (unsigned)nblk, st);
-    case 32: return launch_attn_one<KT, 32>(a, (unsigned)nblk, st);
-    case 64: return launch_attn_one<KT, 64>(a, (unsigned)nblk, st);
-    case 128: return launch_attn_one<KT, 128>(a, (unsigned)nblk, st);
-    default: return launch_attn_one<KT, 0>(a, (unsigned)nblk, st);
+    case 8: return launch_attn_one<64, 8>(a, (unsigned)nblk, st);
+    case 16: return launch_attn_one<64, 16>(a, (unsigned)nblk, st);
+    case 32: return launch_attn_one<64, 32>(a, (unsigned)nblk, st);
+    case 64: return launch_attn_one<64, 64>(a, (unsigned)nblk, st);
+    case 128: return launch_attn_one<64, 128>(a, (unsigned)nblk, st);
+    default: return launch_attn_one<64, 0>(a, (unsigned)nblk, st);
   }
 }
 

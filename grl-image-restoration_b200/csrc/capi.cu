@@ -99,12 +99,13 @@ int grl_coords_table_host(int wh, int ww, int df, float* out) {
 // ---------------------------------------------------------------- fp32 operators
 int grl_bias_table_f32(const float* table, int rows, const float* w1, const float* b1, const float* w2, int hidden,
                        int heads, float* out, void* stream) {
-  return launch_bias_table(table, rows, w1, b1, w2, hidden, heads, 1.0f, out, (cudaStream_t)stream);
+  return launch_bias_table(table, rows, w1, b1, w2, hidden, heads, 1.0f, 1, rows, out, (cudaStream_t)stream);
 }
 
-int grl_bias_table_scaled_f32(const float* table, int rows, const float* w1, const float* b1, const float* w2,
-                              int hidden, int heads, float mul, float* out, void* stream) {
-  return launch_bias_table(table, rows, w1, b1, w2, hidden, heads, mul, out, (cudaStream_t)stream);
+int grl_tc_bias_table4(const float* table, int rows, const float* w1, const float* b1, const float* w2, int hidden,
+                       int heads, float mul, int rows_pad, float* out, void* stream) {
+  GRL_REQUIRE(rows_pad % 4 == 0 && rows_pad >= rows + 4, "tc_bias_table4: rows_pad must be a multiple of 4 and >= rows + 4");
+  return launch_bias_table(table, rows, w1, b1, w2, hidden, heads, mul, 4, rows_pad, out, (cudaStream_t)stream);
 }
 
 int grl_affine_f32(float* attn, int64_t B_, int heads, int n1, int n2, const float* logit_scale, const float* bias,
@@ -276,7 +277,7 @@ int grl_tc_attn(const GrlTcAttn* p, void* stream) {
   a.k = (const __nv_bfloat16*)p->k, a.ldk = p->ldk, a.k_off = p->k_off;
   a.v = (const __nv_bfloat16*)p->v, a.ldv = p->ldv, a.v_off = p->v_off, a.v_dense = p->v_dense;
   a.out = (__nv_bfloat16*)p->out, a.ldo = p->ldo, a.o_off = p->o_off, a.o_dense = p->o_dense;
-  a.B = p->B, a.heads = p->heads, a.bias = p->bias, a.rows = p->rows, a.use_mask = p->use_mask;
+  a.B = p->B, a.heads = p->heads, a.bias = p->bias, a.rows = p->rows, a.rows_pad = p->rows_pad, a.use_mask = p->use_mask;
   GRL_REQUIRE((p->ldq % 8) == 0 && (p->ldk % 8) == 0 && (p->v_dense || (p->ldv % 8) == 0) &&
                   (p->o_dense || (p->ldo % 8) == 0) && (p->q_off % 8) == 0 && (p->k_off % 8) == 0 &&
                   (p->v_off % 8) == 0 && (p->o_off % 8) == 0,

@@ -171,6 +171,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int et = threadIdx.x - 64;  // 0..127
     const int fmt = a.fmt;
     uint16_t* out16 = reinterpret_cast<uint16_t*>(a.out_bf16);
+    // While the main loop runs these warps are idle: pull this tile's residual / CAB rows from DRAM into L2 so that
+    // phase B's loads are L2 hits (the tile is 128 rows x <= 720 B + 384 B).
+    if (a.epi_mode == 1 && a.res_f32) {
+      const long long ptok = s_tok[row];
+      if (ptok >= 0) {
+        const int cw = (EPI == EPI_LN) ? a.C : a.N_f32;
+        const char* rp = reinterpret_cast<const char*>(a.res_f32 + ptok * a.ldr);
+        for (int off = 0; off < cw * 4; off += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + off));
+        if (EPI == EPI_LN && a.cab_y) {
+          const char* cp = reinterpret_cast<const char*>(reinterpret_cast<const uint16_t*>(a.cab_y) + ptok * a.ld_caby);
+          for (int off = 0; off < cw * 2; off += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(cp + off));
+        }
+      }
+    }
     mbar_wait(tmem_full, 0);  // all MMAs done -> accumulators valid AND the pipeline smem is free for staging
     tcgen05_fence_after();
     const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);

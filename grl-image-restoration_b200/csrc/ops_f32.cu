@@ -19,7 +19,7 @@ constexpr int kMaxHeads = 8;
 
 __global__ void bias_table_kernel(const float* __restrict__ table, int rows, const float* __restrict__ w1,
                                   const float* __restrict__ b1, const float* __restrict__ w2, int hidden, int heads,
-                                  float mul, float* __restrict__ out) {
+                                  float mul, int copies, int rows_pad, float* __restrict__ out) {
   extern __shared__ float sm[];  // w1 (hidden*2) | b1 (hidden) | w2 (heads*hidden)
   float* s_w1 = sm;
   float* s_b1 = sm + 2 * hidden;
@@ -43,7 +43,10 @@ __global__ void bias_table_kernel(const float* __restrict__ table, int rows, con
   }
 #pragma unroll
   for (int h = 0; h < kMaxHeads; ++h)
-    if (h < heads) out[(size_t)h * rows + r] = (16.f / (1.f + expf(-acc[h]))) * mul;
+    if (h < heads) {
+      const float val = (16.f / (1.f + expf(-acc[h]))) * mul;
+      for (int c = 0; c < copies; ++c) out[((size_t)h * copies + c) * rows_pad + r + c] = val;  // copy c: shifted by c
+    }
 }
 
 // =====================================================================================
@@ -398,12 +401,13 @@ __global__ void __launch_bounds__(kQT) attn_f32_kernel(AttnArgs a) {
 // host launchers
 // -------------------------------------------------------------------------------------
 int launch_bias_table(const float* table, int rows, const float* w1, const float* b1, const float* w2, int hidden,
-                      int heads, float mul, float* out, cudaStream_t st) {
+                      int heads, float mul, int copies, int rows_pad, float* out, cudaStream_t st) {
+  GRL_REQUIRE(copies >= 1 && copies <= 4 && rows_pad >= rows + copies - 1, "bias_table: bad copies / pitch");
   GRL_REQUIRE(heads >= 1 && heads <= kMaxHeads, "bias_table: heads=%d unsupported (max %d)", heads, kMaxHeads);
   GRL_REQUIRE(rows > 0 && hidden > 0, "bias_table: empty");
   size_t smem = sizeof(float) * (size_t)(3 + heads) * hidden;
   GRL_REQUIRE(smem <= 48 * 1024, "bias_table: hidden=%d too large", hidden);
-  bias_table_kernel<<<ceil_div(rows, 128), 128, smem, st>>>(table, rows, w1, b1, w2, hidden, heads, mul, out);
+  bias_table_kernel<<<ceil_div(rows, 128), 128, smem, st>>>(table, rows, w1, b1, w2, hidden, heads, mul, copies, rows_pad, out);
   GRL_LAUNCH_CHECK("bias_table_kernel");
   return GRL_OK;
 }

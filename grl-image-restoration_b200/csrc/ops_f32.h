@@ -46,7 +46,7 @@ struct AttnArgs {
 };
 
 int launch_bias_table(const float* table, int rows, const float* w1, const float* b1, const float* w2, int hidden,
-                      int heads, float mul, float* out, cudaStream_t st);
+                      int heads, float mul, int copies, int rows_pad, float* out, cudaStream_t st);
 int launch_affine(float* attn, long long B_, int heads, int n1, int n2, const float* logit_scale, const float* bias,
                   int rows, const long long* index, const float* mask, int nW, cudaStream_t st);
 int launch_gemm(const GemmArgs& a, bool conv, cudaStream_t st);

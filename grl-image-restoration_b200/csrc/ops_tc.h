@@ -72,8 +72,8 @@ struct AttnTcArgs {
   int o_off;
   int o_dense;
   int B, heads;
-  const float* bias;  // (heads, rows) fp32, log2 domain
-  int rows;
+  const float* bias;  // (heads, 4, rows_pad) fp32, log2 domain: copy c holds the table shifted right by c entries
+  int rows, rows_pad;
   int use_mask;
 };
 int launch_attn_tc(const AttnTcArgs& a, cudaStream_t st);

@@ -130,17 +130,35 @@ def attention(gq, gk, q, q_off, k, k_off, v, v_off, out, o_off, B, heads, bias, 
     p.k, p.ldk, p.k_off = k.data_ptr(), k.shape[-1], k_off
     p.v, p.ldv, p.v_off, p.v_dense = v.data_ptr(), v.shape[-1], v_off, int(v_dense)
     p.out, p.ldo, p.o_off, p.o_dense = out.data_ptr(), out.shape[-1], o_off, int(o_dense)
-    p.B, p.heads, p.bias, p.rows, p.use_mask = B, heads, bias.data_ptr(), bias.shape[1], int(use_mask)
+    if bias.dim() != 3 or bias.shape[1] != 4:
+        raise RuntimeError("grl_b200: attention bias must be the (heads, 4, rows_pad) table of bias_table_log2 / shifted_copies")
+    p.B, p.heads, p.bias, p.use_mask = B, heads, bias.data_ptr(), int(use_mask)
+    p.rows, p.rows_pad = (gq.wh + gk.wh - 1) * (gq.ww + gk.ww - 1), bias.shape[2]
     K._timed(tag, lambda: capi.check(capi.lib().grl_tc_attn(ctypes.byref(p), capi.stream())))
 
 
+def bias_rows_pad(rows):
+    return round_up(rows + 4, 4)
+
+
+def shifted_copies(table_hr):
+    """(heads, rows) fp32 -> (heads, 4, rows_pad): copy c shifted right by c entries (layout grl_tc_attn reads)."""
+    heads, rows = table_hr.shape
+    out = torch.zeros(heads, 4, bias_rows_pad(rows), device=table_hr.device, dtype=torch.float32)
+    for c in range(4):
+        out[:, c, c:c + rows] = table_hr
+    return out
+
+
 def bias_table_log2(transform, table):
+    """16*sigmoid(cpb_mlp(table))*log2(e) as the 4-copy table of the attention kernel."""
     t = table.reshape(-1, 2)
     w1, b1, w2 = transform.cpb_mlp[0].weight, transform.cpb_mlp[0].bias, transform.cpb_mlp[2].weight
     heads, hidden = w2.shape
-    out = torch.empty(heads, t.shape[0], device=t.device, dtype=torch.float32)
-    capi.check(capi.lib().grl_bias_table_scaled_f32(capi.ptr(t), t.shape[0], capi.ptr(w1), capi.ptr(b1), capi.ptr(w2),
-                                                    hidden, heads, LOG2E, capi.ptr(out), capi.stream()))
+    rows_pad = bias_rows_pad(t.shape[0])
+    out = torch.zeros(heads, 4, rows_pad, device=t.device, dtype=torch.float32)
+    capi.check(capi.lib().grl_tc_bias_table4(capi.ptr(t), t.shape[0], capi.ptr(w1), capi.ptr(b1), capi.ptr(w2), hidden,
+                                             heads, LOG2E, rows_pad, capi.ptr(out), capi.stream()))
     return out
 
 

@@ -126,9 +126,12 @@ int grl_stripe_attn_f32(const float* qkv, int64_t ld_qkv, const float* anchor, i
  * Activations are bf16 with channel pitches padded to a multiple of 64; attention heads live in 32-wide "slots"
  * (head_dim zero-padded to 32).  The residual stream, LayerNorm, softmax statistics and all accumulators stay fp32. */
 
-/* grl_bias_table_f32 with the table multiplied by `mul` (log2(e) for the exp2-domain softmax of grl_tc_attn). */
-int grl_bias_table_scaled_f32(const float* table, int rows, const float* w1, const float* b1, const float* w2,
-                              int hidden, int heads, float mul, float* out, void* stream);
+/* grl_bias_table_f32 scaled by `mul` (log2(e) for the exp2-domain softmax of grl_tc_attn) and written as FOUR
+ * copies, copy c shifted right by c entries: out[(h*4 + c)*rows_pad + r + c] = bias[h][r].  `out` (heads, 4, rows_pad)
+ * must be zero-initialised; rows_pad % 4 == 0, rows_pad >= rows + 4.  The attention kernel reads runs of four
+ * consecutive table entries as one aligned 16-byte load from the copy that matches the run's alignment. */
+int grl_tc_bias_table4(const float* table, int rows, const float* w1, const float* b1, const float* w2, int hidden,
+                       int heads, float mul, int rows_pad, float* out, void* stream);
 
 /* `fmt` selects the 16-bit operand format everywhere below: 0 = fp16 (default: 11-bit mantissa, saturating
  * converts; needed for the 0.01 dB PSNR gate), 1 = bf16.  Both run kind::f16 tcgen05.mma at the same rate. */
@@ -189,7 +192,7 @@ int grl_tc_gemm(const GrlTcGemm* p, void* stream);
 /* Fused cosine attention over packed bf16 head slots: out = softmax2(q k^T + bias + mask) v, one call per
  * WindowAttention.forward and two per AnchorStripeAttention.forward (efficient.py:128-165,:215-270).
  * q/k/v: bf16 token rows (pitch ld*, element offset *_off of head 0's slot); v_dense/o_dense: the (B_, heads, N, 32)
- * intermediate X1 of the stripe attention; bias: (heads, rows) fp32 from grl_bias_table_scaled_f32(.., log2 e). */
+ * intermediate X1 of the stripe attention; bias: (heads, 4, rows_pad) fp32 from grl_tc_bias_table4(.., log2 e, ..). */
 typedef struct {
   int32_t fmt; /* 0 = fp16, 1 = bf16 */
   GrlGrid gq, gk;
@@ -208,8 +211,9 @@ typedef struct {
   int32_t o_off;
   int32_t o_dense;
   int32_t B, heads;
-  const float* bias;
+  const float* bias; /* (heads, 4, rows_pad) from grl_tc_bias_table4 */
   int32_t rows;
+  int32_t rows_pad;
   int32_t use_mask;
 } GrlTcAttn;
 int grl_tc_attn(const GrlTcAttn* p, void* stream);

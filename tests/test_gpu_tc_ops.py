@@ -159,7 +159,7 @@ def test_attention_tc_window(tc, oracle, device, B, H, W, ws, heads, shifted, fm
     q16 = qkv.view(B * L, nsl * 32).to(device).to(tc.DTYPE[fmt])
     out = torch.zeros(B * L, heads * 32, device=device, dtype=tc.DTYPE[fmt])
     grid = G.token_grid((H, W), ws, (s, s))
-    tc.attention(grid, grid, q16, 0, q16, heads * 32, q16, 2 * heads * 32, out, 0, B, heads, table.to(device), shifted)
+    tc.attention(grid, grid, q16, 0, q16, heads * 32, q16, 2 * heads * 32, out, 0, B, heads, tc.shifted_copies(table.to(device)), shifted)
     got = out.cpu().float().view(B, L, heads * 32)
     err = (got - ref).abs().max().item()
     assert err <= 4e-2 * max(1.0, ref.abs().max().item()), err
@@ -208,8 +208,8 @@ def test_attention_tc_stripe_chain(tc, oracle, device, B, H, W, stripe, df, head
     nW = (H // ss[0]) * (W // ss[1])
     x1d = torch.empty(B * nW * heads * ass[0] * ass[1], 32, device=device, dtype=torch.float16)
     out = torch.zeros(B * L, heads * 32, device=device, dtype=torch.float16)
-    tc.attention(ag, tok, a16, 0, q16, heads * 32, q16, 2 * heads * 32, x1d, 0, B, heads, t1.to(device), shifted, o_dense=True)
-    tc.attention(tok, ag, q16, 0, a16, 0, x1d, 0, out, 0, B, heads, t2.to(device), shifted, v_dense=True)
+    tc.attention(ag, tok, a16, 0, q16, heads * 32, q16, 2 * heads * 32, x1d, 0, B, heads, tc.shifted_copies(t1.to(device)), shifted, o_dense=True)
+    tc.attention(tok, ag, q16, 0, a16, 0, x1d, 0, out, 0, B, heads, tc.shifted_copies(t2.to(device)), shifted, v_dense=True)
     got = out.cpu().float().view(B, L, heads * 32)
     assert (x1d.cpu().float().view(x1.shape) - x1).abs().max().item() <= 4e-2 * max(1.0, x1.abs().max().item())
     err = (got - ref).abs().max().item()
