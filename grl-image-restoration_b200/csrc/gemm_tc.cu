@@ -19,6 +19,8 @@
 //                  (F.normalize + logit scale of Attention.attn / AffineTransform, efficient.py:39,:85)
 //   EPI_LN       : x' = x + rs * LayerNorm(acc + b) (+ cab_y * gate) -> fp32 residual stream + bf16 operand copy
 //                  (efficient.py:543-554)
+#include <stdlib.h>
+
 #include "grl_common.cuh"
 #include "tc_common.cuh"
 #include "ops_tc.h"
@@ -56,7 +58,7 @@ struct GemmSmem {
   static constexpr int B_BYTES = BN * kBK * 2;
   static constexpr int STAGE = A_BYTES + B_BYTES;
   static constexpr int PIPE = kStages * STAGE;
-  static constexpr int STG32 = kBM * stage_pitch32(BN <= 192 ? (BN == 192 ? 188 : BN) : 4) * 4;  // C <= 188 at BN = 192
+  static constexpr int STG32 = (BN == 96) ? 0 : kBM * stage_pitch32(BN <= 192 ? (BN == 192 ? 188 : BN) : 4) * 4;  // C <= 188 at BN = 192
   static constexpr int STG16 = kBM * (BN + 8) * 2;
   static constexpr int STG = (STG32 > STG16 ? STG32 : STG16);
   static constexpr int OFF_TOK = ((PIPE > STG ? PIPE : STG) + 15) / 16 * 16;  // long long tok[128]
@@ -69,7 +71,7 @@ __device__ __forceinline__ uint32_t tmem_cols_for(int bn) { return bn <= 32 ? 32
 __device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
 template <int BN, int EPI, bool CONV>
-__global__ void __launch_bounds__(192, 2)
+__global__ void __launch_bounds__(192, (BN <= 96 ? 3 : 2))
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmTcArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -412,6 +414,7 @@ static int dispatch_bn(int bn, const CUtensorMap& tmA, const CUtensorMap& tmB, c
                        cudaStream_t st) {
   switch (bn) {
     case 64: return launch_one<64, EPI, CONV>(tmA, tmB, a, grid, st);
+    case 96: return launch_one<96, EPI, CONV>(tmA, tmB, a, grid, st);
     case 128: return launch_one<128, EPI, CONV>(tmA, tmB, a, grid, st);
     case 192: return launch_one<192, EPI, CONV>(tmA, tmB, a, grid, st);
     case 256: return launch_one<256, EPI, CONV>(tmA, tmB, a, grid, st);
@@ -431,7 +434,14 @@ int pick_bn(int npad) {
 int launch_gemm_tc(const GemmTcProblem& p, GemmTcArgs a, cudaStream_t st) {
   GRL_REQUIRE(p.kpad % kBK == 0 && p.kpad > 0, "gemm_tc: K pad %d must be a multiple of 64", p.kpad);
   GRL_REQUIRE(p.npad % 32 == 0 && p.npad > 0, "gemm_tc: N pad %d must be a multiple of 32", p.npad);
-  const int bn = (p.epi == EPI_LN) ? (p.npad <= 64 ? 64 : p.npad <= 128 ? 128 : p.npad <= 192 ? 192 : 256) : pick_bn(p.npad);
+  int bn = (p.epi == EPI_LN) ? (p.npad <= 64 ? 64 : p.npad <= 128 ? 128 : p.npad <= 192 ? 192 : 256) : pick_bn(p.npad);
+  // 16-bit-only epilogues (QKV, fc1, CAB conv2): 96-wide tiles need 58 KB smem / 128 TMEM columns -> 3 CTAs per SM
+  static int narrow = -1;
+  if (narrow < 0) {
+    const char* e = getenv("GRL_GEMM_BN96");
+    narrow = (e && e[0] == '1') ? 1 : 0;  // opt-in: measured no gain on B200 (profiles/r1_tc_path_final.md)
+  }
+  if (narrow && p.epi != EPI_LN && !a.out_f32 && !a.res_f32 && p.npad % 96 == 0 && p.npad >= 192) bn = 96;
   GRL_REQUIRE(p.epi != EPI_LN || p.npad <= 256, "gemm_tc: LayerNorm epilogue needs the whole row in one tile (N=%d)",
               p.npad);
   const bool conv = p.taps == 9;
@@ -443,7 +453,7 @@ int launch_gemm_tc(const GemmTcProblem& p, GemmTcArgs a, cudaStream_t st) {
     const int cw = p.epi == EPI_LN ? a.C : a.N_f32;
     const int cap = bn == 64 ? GemmSmem<64>::OFF_TOK : bn == 128 ? GemmSmem<128>::OFF_TOK : bn == 192 ? GemmSmem<192>::OFF_TOK
                                                                                                      : GemmSmem<256>::OFF_TOK;
-    const bool ok = p.npad <= bn && cw > 0 && cw % 4 == 0 && kBM * stage_pitch32(cw) * 4 <= cap &&
+    const bool ok = bn != 96 && p.npad <= bn && cw > 0 && cw % 4 == 0 && kBM * stage_pitch32(cw) * 4 <= cap &&
                     (!a.out_f32 || a.ldo_f32 % 4 == 0) && (!a.res_f32 || a.ldr % 4 == 0) &&
                     (!a.out_bf16 || a.ldo_bf16 % 4 == 0);
     GRL_REQUIRE(ok || p.epi != EPI_LN, "gemm_tc: LayerNorm epilogue needs C %% 4 == 0 and C <= 188 (got %d)", cw);
