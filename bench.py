@@ -21,6 +21,9 @@ import torch
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# keep stdout to the single JSON line: NCCL prints its version banner to stdout at NCCL_DEBUG=VERSION
+if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+    os.environ["NCCL_DEBUG"] = "WARN"
 
 WORKLOADS = {
     # name: (variant, task, scale, tile, tiles per GPU)

@@ -62,7 +62,8 @@ struct GemmSmem {
   static constexpr int STG16 = kBM * (BN + 8) * 2;
   static constexpr int STG = (STG32 > STG16 ? STG32 : STG16);
   static constexpr int OFF_TOK = ((PIPE > STG ? PIPE : STG) + 15) / 16 * 16;  // long long tok[128]
-  static constexpr int OFF_BAR = OFF_TOK + 128 * 8;
+  static constexpr int OFF_PAR = OFF_TOK + 128 * 8 + 128 * 4;  // (+ int img[128]) float bias[BN], gamma[BN], beta[BN]
+  static constexpr int OFF_BAR = OFF_PAR + 3 * BN * 4;
   static constexpr int TOTAL = OFF_BAR + 128 + 1024 /*align slack*/;
 };
 
@@ -81,6 +82,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* tmem_full = empty + kStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
   long long* s_tok = reinterpret_cast<long long*>(smem + S::OFF_TOK);
+  int* s_img = reinterpret_cast<int*>(smem + S::OFF_TOK + 128 * 8);  // image (batch) index of every row (CAB gate)
+  float* s_bias = reinterpret_cast<float*>(smem + S::OFF_PAR);      // this tile's columns [n0, n0 + BN)
+  float* s_gamma = s_bias + BN;
+  float* s_beta = s_gamma + BN;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = blockIdx.y * BN;
@@ -111,6 +116,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tma_prefetch_desc(&tmB);
   }
   if (warp == 1) tmem_alloc(tmem_slot, tmem_cols_for(BN));
+  // per-column constants once per CTA (every row-owner thread needs all of them: smem broadcast instead of a global
+  // load per accumulator element)
+  for (int c = threadIdx.x; c < BN; c += blockDim.x) {
+    const int n = n0 + c;
+    s_bias[c] = (n < a.N) ? a.bias[n] : 0.f;
+    if (EPI == EPI_LN) {
+      s_gamma[c] = (c < a.C) ? a.gamma[c] : 0.f;
+      s_beta[c] = (c < a.C) ? a.beta[c] : 0.f;
+    }
+  }
   if (warp >= 2) {  // token (global row) of every accumulator row, -1 = outside the problem
     const int r = (warp & 3) * 32 + lane;
     long long tok;
@@ -122,6 +137,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (tok >= a.M) tok = -1;
     }
     s_tok[r] = tok;
+    s_img[r] = (EPI == EPI_LN && tok >= 0) ? (int)(tok / a.L) : 0;  // one 64-bit division per row, not per access
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -205,7 +221,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           const int n = n0 + c0 + j;
-          float val = apply_act(__uint_as_float(v[j]) + (n < a.N ? __ldg(a.bias + n) : 0.f), a.act, a.slope);
+          float val = apply_act(__uint_as_float(v[j]) + s_bias[c0 + j], a.act, a.slope);
           if (a.res_f32 && n < a.N_f32) val += __ldg(a.res_f32 + tok * a.ldr + n);
           o[j] = (n < a.N) ? val : 0.f;
           if (a.out_f32 && n < a.N_f32) a.out_f32[tok * a.ldo_f32 + n] = o[j];
@@ -225,26 +241,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       float* stg = reinterpret_cast<float*>(smem);
       // ---------------- phase A
       if (EPI == EPI_LN) {
-        float sum = 0.f;
+        // one pass over TMEM for both moments, shifted by the row's first element (no catastrophic cancellation):
+        //   mean = x0 + S1/C,  var = S2/C - (S1/C)^2   with S1 = sum(x - x0), S2 = sum((x - x0)^2)
+        float s1 = 0.f, s2 = 0.f, x0 = 0.f;
         for (int c0 = 0; c0 < Cw; c0 += 32) {
           tmem_ld32(trow + c0, v);
           tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (c0 + j < Cw) sum += __uint_as_float(v[j]) + __ldg(a.bias + c0 + j);
-        }
-        const float mean = sum / (float)Cw;
-        float var = 0.f;
-        for (int c0 = 0; c0 < Cw; c0 += 32) {
-          tmem_ld32(trow + c0, v);
-          tmem_ld_wait();
+          if (c0 == 0) x0 = __uint_as_float(v[0]) + s_bias[0];
 #pragma unroll
           for (int j = 0; j < 32; ++j)
             if (c0 + j < Cw) {
-              const float d = __uint_as_float(v[j]) + __ldg(a.bias + c0 + j) - mean;
-              var = fmaf(d, d, var);
+              const float d = __uint_as_float(v[j]) + s_bias[c0 + j] - x0;
+              s1 += d;
+              s2 = fmaf(d, d, s2);
             }
         }
+        const float m1 = s1 / (float)Cw;
+        const float mean = x0 + m1;
+        const float var = fmaxf(s2 / (float)Cw - m1 * m1, 0.f) * (float)Cw;  // (kept as a sum for the line below)
         const float rstd = rsqrtf(var / (float)Cw + a.eps);
         for (int c0 = 0; c0 < Cw; c0 += 32) {
           tmem_ld32(trow + c0, v);
@@ -255,8 +269,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const int c = c0 + j + e;
-              o4[e] = (c < Cw) ? ((__uint_as_float(v[j + e]) + __ldg(a.bias + c) - mean) * rstd * __ldg(a.gamma + c) +
-                                  __ldg(a.beta + c)) * a.res_scale
+              o4[e] = (c < Cw) ? ((__uint_as_float(v[j + e]) + s_bias[c] - mean) * rstd * s_gamma[c] + s_beta[c]) * a.res_scale
                                : 0.f;
             }
             if (c0 + j < pitch) *reinterpret_cast<float4*>(stg + row * pitch + c0 + j) = make_float4(o4[0], o4[1], o4[2], o4[3]);
@@ -272,7 +285,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const int n = c0 + j + e;
-              o4[e] = (n < a.N) ? apply_act(__uint_as_float(v[j + e]) + __ldg(a.bias + n), a.act, a.slope) : 0.f;
+              o4[e] = (n < a.N) ? apply_act(__uint_as_float(v[j + e]) + s_bias[n], a.act, a.slope) : 0.f;
             }
             if (c0 + j < pitch) *reinterpret_cast<float4*>(stg + row * pitch + c0 + j) = make_float4(o4[0], o4[1], o4[2], o4[3]);
           }
@@ -306,7 +319,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               if (a.res_f32) rr[i] = __ldg(reinterpret_cast<const float4*>(a.res_f32 + tok[i] * a.ldr + c4 * 4));
               if (has_cab) {
                 cy[i] = __ldg(reinterpret_cast<const uint2*>(caby + tok[i] * a.ld_caby + c4 * 4));
-                gg[i] = __ldg(reinterpret_cast<const float4*>(a.cab_gate + (tok[i] / a.L) * Cw + c4 * 4));
+                gg[i] = __ldg(reinterpret_cast<const float4*>(a.cab_gate + (long long)s_img[ew + 4 * (rb + i)] * Cw + c4 * 4));
               }
             }
           }
@@ -344,7 +357,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           float ss = 0.f;
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            o[j] = __uint_as_float(v[j]) + __ldg(a.bias + n0 + c0 + j);
+            o[j] = __uint_as_float(v[j]) + s_bias[c0 + j];
             ss = fmaf(o[j], o[j], ss);
           }
           const float sc = __ldg(a.slot_scale + slot);
@@ -353,7 +366,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int j = 0; j < 32; ++j) o[j] *= mul;
         } else {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) o[j] = apply_act(__uint_as_float(v[j]) + __ldg(a.bias + n0 + c0 + j), a.act, a.slope);
+          for (int j = 0; j < 32; ++j) o[j] = apply_act(__uint_as_float(v[j]) + s_bias[c0 + j], a.act, a.slope);
         }
 #pragma unroll
         for (int j = 0; j < 32; j += 8)
