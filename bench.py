@@ -263,9 +263,19 @@ def main():
     attn_launches = sum(v[1] for v in attn_ms.values())
     flops_timed = counts["f_attn"] * (hi - lo) * a.steps  # this rank's images
     achieved = flops_timed / (attn_total_ms / 1e3) / 1e12 if attn_total_ms > 0 else 0.0
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if precision != "fp32" and a.workload == "cfg4" and os.path.exists(tpath):
+        with open(tpath) as f:
+            tj = json.load(f)
+        # per-launch DRAM bytes (ncu dram__bytes_read + write of one capture, scaled to this rank's tiles per launch)
+        traffic = tj["attention_dram_bytes_per_image_per_block"] * (hi - lo) / tj["launches_per_block"]
     roof = {"bound": "tensor", "kernel": "fused window + anchored-stripe attention (QK^T + PV)",
             "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tflops"],
-            "peak_source": f"bf16 sustained, {pk['src']}", "traffic": None,
+            "peak_source": f"bf16 sustained, {pk['src']}", "traffic": traffic,
+            "traffic_note": "average DRAM bytes per attention launch from profiles/traffic.json (one ncu --set full capture)",
+            "co_bound": "softmax: 16 MUFU ex2/clk/SM and ~12 SIMT instructions per score element cap this kernel at "
+                        "~25 % of the tensor pipe at head_dim 32 (DESIGN.md section 5)",
             "share_of_step": attn_total_ms / ms_total, "launches_timed": attn_launches,
             "algorithmic_gflop_per_image": counts["f_attn"] / 1e9, "qk_frac": achieved / 2 / pk["tflops"],
             "whole_model_tflops": None}

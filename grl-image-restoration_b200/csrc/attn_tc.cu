@@ -49,7 +49,7 @@ struct AttnSmem {
   static constexpr int OFF_META = OFF_P + 2 * P_BYTES;                       // int koff[3][KT], rid[3][KT] (tile % 3)
   static constexpr int OFF_BAR = OFF_META + 6 * KT * 4;
   static constexpr int TOTAL = OFF_BAR + 128 + 1024;
-  static_assert(P_BYTES % 1024 == 0, "P tiles must be 1024-byte aligned for SWIZZLE_128B");
+  static_assert(P_BYTES % 1024 == 0, "P tiles must be 1024-byte aligned");
 };
 
 constexpr int kAttnThreads = kQT + 32;  // 4 softmax warps (one query row per thread) + 1 producer / MMA warp
@@ -64,8 +64,8 @@ constexpr int kAttnThreads = kQT + 32;  // 4 softmax warps (one query row per th
 // KW: key-window width when it is a power of two >= 8 (bias rows read as aligned float4 from the 4-way shifted table
 // copies), 0 = generic scalar path.
 template <int KT, int KW>
-__global__ void __launch_bounds__(kAttnThreads, 3) attn_tc_kernel(const AttnTcArgs a) {
-  static_assert(KT == 64 || KT == 128, "P tiles are 128-byte rows (64 keys) with SWIZZLE_128B");
+__global__ void __launch_bounds__(kAttnThreads, (KT <= 32 ? 4 : KT <= 64 ? 3 : 2)) attn_tc_kernel(const AttnTcArgs a) {
+  static_assert(KT == 32 || KT == 64 || KT == 128, "P tiles: 64-byte rows (SWIZZLE_64B) or 128-byte rows (SWIZZLE_128B)");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   using S = AttnSmem<KT>;
@@ -97,8 +97,7 @@ __global__ void __launch_bounds__(kAttnThreads, 3) attn_tc_kernel(const AttnTcAr
   const int wr = w / nww, wc = w - wr * nww;
   const int Wt = a.gq.ww + a.gk.ww - 1;
   const int ntiles = (Nk + KT - 1) / KT;
-  constexpr uint32_t TMEM_COLS = (KT + kDP <= 64) ? 64 : 128;
-  static_assert(KT + kDP <= 128, "S + O must fit 128 TMEM columns");
+  constexpr uint32_t TMEM_COLS = (KT + kDP <= 64) ? 64 : (KT + kDP <= 128) ? 128 : 256;
 
   if (tid == 0) {
     mbar_init(bar_s, 1);
@@ -169,9 +168,15 @@ __global__ void __launch_bounds__(kAttnThreads, 3) attn_tc_kernel(const AttnTcAr
         umma_ss(tmem, umma_desc(q_sa + k * 32, 16, 512, SWZ_64B), umma_desc(k_sa + k * 32, 16, 512, SWZ_64B), idesc_qk, k != 0);
       umma_commit(bar_s);
     };
-    // all of this warp's outstanding gathers have landed and are visible to the tensor core (async proxy)
-    auto publish_loads = [&]() {
+    // this warp's gathers -- all of them, or all but the most recently committed group -- have landed and are
+    // visible to the tensor core (async proxy)
+    auto publish_all = [&]() {
       cp_async_wait<0>();
+      fence_proxy_async_smem();
+      __syncwarp();
+    };
+    auto publish_but_last = [&]() {
+      cp_async_wait<1>();
       fence_proxy_async_smem();
       __syncwarp();
     };
@@ -181,15 +186,16 @@ __global__ void __launch_bounds__(kAttnThreads, 3) attn_tc_kernel(const AttnTcAr
     if (ntiles > 1) load_k(1);
     load_v(0);
     cp_async_commit();
-    publish_loads();
+    publish_all();
     if (lane == 0) {
       tcgen05_fence_after();
       issue_qk(0);
     }
     for (int t = 0; t < ntiles; ++t) {
       // ---- QK(t+1): K_{t+1} was requested an iteration ago; the S columns are free once every row has read S_t
+      // commit order per iteration is  {K_{t+2}}, {V_{t+1}}:  K_{t+1} is in the second most recent group here
       if (t + 1 < ntiles) {
-        publish_loads();
+        publish_but_last();
         mbar_wait(s_free, t & 1);
         if (lane == 0) {
           tcgen05_fence_after();
@@ -199,8 +205,9 @@ __global__ void __launch_bounds__(kAttnThreads, 3) attn_tc_kernel(const AttnTcAr
       // K buffer t&1 is free (QK(t) completed before anyone could read S_t)
       if (t + 2 < ntiles) load_k(t + 2);
       cp_async_commit();
-      // ---- PV(t): V_t landed; P_t written and O_{t-1} consumed by every row
-      publish_loads();
+      // ---- PV(t): V_t landed (second most recent group; K_{t+2} may still be in flight); P_t written and O_{t-1}
+      // consumed by every row
+      publish_but_last();
       mbar_wait(p_full, t & 1);
       if (lane == 0) {
         tcgen05_fence_after();
@@ -208,8 +215,9 @@ __global__ void __launch_bounds__(kAttnThreads, 3) attn_tc_kernel(const AttnTcAr
         const uint32_t pt_sa = p_sa + (t & 1) * S::P_BYTES;
 #pragma unroll
         for (int k = 0; k < KT / 16; ++k) {
-          const uint32_t pa = pt_sa + (k >> 2) * (kQT * 128) + (k & 3) * 32;
-          umma_ss(tmem + KT, umma_desc(pa, 16, 1024, SWZ_128B), umma_desc(v_sa + k * 1024, 16, 512, SWZ_64B), idesc_pv, k != 0);
+          const uint64_t pd = (KT == 32) ? umma_desc(pt_sa + k * 32, 16, 512, SWZ_64B)
+                                         : umma_desc(pt_sa + (k >> 2) * (kQT * 128) + (k & 3) * 32, 16, 1024, SWZ_128B);
+          umma_ss(tmem + KT, pd, umma_desc(v_sa + k * 1024, 16, 512, SWZ_64B), idesc_pv, k != 0);
         }
         umma_commit(bar_o);
       }
@@ -314,9 +322,12 @@ __global__ void __launch_bounds__(kAttnThreads, 3) attn_tc_kernel(const AttnTcAr
           pk = make_uint4(pack_bf16(p[0], p[1]), pack_bf16(p[2], p[3]), pack_bf16(p[4], p[5]), pack_bf16(p[6], p[7]));
         else
           pk = make_uint4(pack_f16(p[0], p[1]), pack_f16(p[2], p[3]), pack_f16(p[4], p[5]), pack_f16(p[6], p[7]));
-        // [128 x KT] K-major SWIZZLE_128B, 64-key sub-tiles of 16 KB
-        const int sub = c >> 3, cc = c & 7;
-        *reinterpret_cast<uint4*>(Pt + sub * (kQT * 128) + tid * 128 + ((cc ^ (tid & 7)) << 4)) = pk;
+        if (KT == 32) {  // [128 x 32] K-major: 64-byte rows, SWIZZLE_64B
+          *reinterpret_cast<uint4*>(Pt + sw64(tid, c)) = pk;
+        } else {  // [128 x KT] K-major SWIZZLE_128B, 64-key sub-tiles of 16 KB
+          const int sub = c >> 3, cc = c & 7;
+          *reinterpret_cast<uint4*>(Pt + sub * (kQT * 128) + tid * 128 + ((cc ^ (tid & 7)) << 4)) = pk;
+        }
       }
       l_run = l_run * corr + ((ps[0] + ps[1]) + (ps[2] + ps[3]));
 
@@ -388,14 +399,28 @@ int launch_attn_tc(const AttnTcArgs& a, cudaStream_t st) {
   const int Nq = a.gq.wh * a.gq.ww;
   const long long nblk = (long long)a.B * (a.gq.H / a.gq.wh) * (a.gq.W / a.gq.ww) * a.heads * ceil_div(Nq, kQT);
   GRL_REQUIRE(nblk < (1ll << 31), "attn_tc: grid too large");
-  switch (a.gk.ww) {
-    case 8: return launch_attn_one<64, 8>(a, (unsigned)nblk, st);
-    case 16: return launch_attn_one<64, 16>(a, (unsigned)nblk, st);
-    case 32: return launch_attn_one<64, 32>(a, (unsigned)nblk, st);
-    case 64: return launch_attn_one<64, 64>(a, (unsigned)nblk, st);
-    case 128: return launch_attn_one<64, 128>(a, (unsigned)nblk, st);
-    default: return launch_attn_one<64, 0>(a, (unsigned)nblk, st);
+  static int kt = 0;  // keys per tile: 64 (3 CTAs / SM) or 128 via GRL_ATTN_KT=128 (2 CTAs / SM, half the hand-offs)
+  if (kt == 0) {
+    const char* e = getenv("GRL_ATTN_KT");
+    kt = (e && atoi(e) == 128) ? 128 : (e && atoi(e) == 32) ? 32 : 64;
   }
+#define GRL_ATTN_DISPATCH(KTV)                                         \
+  switch (a.gk.ww) {                                                    \
+    case 8: return launch_attn_one<KTV, 8>(a, (unsigned)nblk, st);      \
+    case 16: return launch_attn_one<KTV, 16>(a, (unsigned)nblk, st);    \
+    case 32: return launch_attn_one<KTV, 32>(a, (unsigned)nblk, st);    \
+    case 64: return launch_attn_one<KTV, 64>(a, (unsigned)nblk, st);    \
+    case 128: return launch_attn_one<KTV, 128>(a, (unsigned)nblk, st);  \
+    default: return launch_attn_one<KTV, 0>(a, (unsigned)nblk, st);     \
+  }
+  if (kt == 128) {
+    GRL_ATTN_DISPATCH(128)
+  }
+  if (kt == 32) {
+    GRL_ATTN_DISPATCH(32)
+  }
+  GRL_ATTN_DISPATCH(64)
+#undef GRL_ATTN_DISPATCH
 }
 
 }  // namespace tc

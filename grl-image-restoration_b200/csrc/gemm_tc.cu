@@ -189,20 +189,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int et = threadIdx.x - 64;  // 0..127
     const int fmt = a.fmt;
     uint16_t* out16 = reinterpret_cast<uint16_t*>(a.out_bf16);
-    // While the main loop runs these warps are idle: pull this tile's residual / CAB rows from DRAM into L2 so that
-    // phase B's loads are L2 hits (the tile is 128 rows x <= 720 B + 384 B).
-    if (a.epi_mode == 1 && a.res_f32) {
-      const long long ptok = s_tok[row];
-      if (ptok >= 0) {
-        const int cw = (EPI == EPI_LN) ? a.C : a.N_f32;
-        const char* rp = reinterpret_cast<const char*>(a.res_f32 + ptok * a.ldr);
-        for (int off = 0; off < cw * 4; off += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + off));
-        if (EPI == EPI_LN && a.cab_y) {
-          const char* cp = reinterpret_cast<const char*>(reinterpret_cast<const uint16_t*>(a.cab_y) + ptok * a.ld_caby);
-          for (int off = 0; off < cw * 2; off += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(cp + off));
-        }
-      }
-    }
     mbar_wait(tmem_full, 0);  // all MMAs done -> accumulators valid AND the pipeline smem is free for staging
     tcgen05_fence_after();
     const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
@@ -239,6 +225,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int Cw = (EPI == EPI_LN) ? a.C : a.N_f32;  // real fp32 columns of this tile row (n0 == 0 when wide)
       const int pitch = stage_pitch32(Cw);
       float* stg = reinterpret_cast<float*>(smem);
+      // ---------------- residual tile -> staging, asynchronously (cp.async, 16 B per request, the whole 128 x C
+      // tile in flight at once); it lands while the row moments are computed from TMEM.  Phase A then adds its
+      // result in place, so phase B has no fp32 loads left.
+      const bool res_in_stage = a.res_f32 != nullptr;
+      if (res_in_stage) {
+        const int C4r = Cw >> 2, ewr = et >> 5;
+        for (int r = ewr; r < kBM; r += 4) {
+          const long long rtok = s_tok[r];
+          for (int c4 = lane; c4 < C4r; c4 += 32)
+            cp_async_16(stg + r * pitch + c4 * 4, a.res_f32 + (rtok >= 0 ? rtok : 0) * a.ldr + c4 * 4, rtok >= 0);
+        }
+        cp_async_commit();
+      }
       // ---------------- phase A
       if (EPI == EPI_LN) {
         // one pass over TMEM for both moments, shifted by the row's first element (no catastrophic cancellation):
@@ -260,34 +259,46 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const float mean = x0 + m1;
         const float var = fmaxf(s2 / (float)Cw - m1 * m1, 0.f) * (float)Cw;  // (kept as a sum for the line below)
         const float rstd = rsqrtf(var / (float)Cw + a.eps);
+        if (res_in_stage) {  // every thread's share of the residual tile has landed and is visible to the row owners
+          cp_async_wait<0>();
+          epi_barrier();
+        }
         for (int c0 = 0; c0 < Cw; c0 += 32) {
           tmem_ld32(trow + c0, v);
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
-            float o4[4];
+            if (c0 + j < Cw) {  // Cw % 4 == 0
+              float4* sp = reinterpret_cast<float4*>(stg + row * pitch + c0 + j);
+              float4 acc4 = res_in_stage ? *sp : make_float4(0.f, 0.f, 0.f, 0.f);
+              float o4[4] = {acc4.x, acc4.y, acc4.z, acc4.w};
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int c = c0 + j + e;
-              o4[e] = (c < Cw) ? ((__uint_as_float(v[j + e]) + s_bias[c] - mean) * rstd * s_gamma[c] + s_beta[c]) * a.res_scale
-                               : 0.f;
+              for (int e = 0; e < 4; ++e) {
+                const int c = c0 + j + e;
+                o4[e] += ((__uint_as_float(v[j + e]) + s_bias[c] - mean) * rstd * s_gamma[c] + s_beta[c]) * a.res_scale;
+              }
+              *sp = make_float4(o4[0], o4[1], o4[2], o4[3]);
             }
-            if (c0 + j < pitch) *reinterpret_cast<float4*>(stg + row * pitch + c0 + j) = make_float4(o4[0], o4[1], o4[2], o4[3]);
           }
         }
       } else {
+        if (res_in_stage) {
+          cp_async_wait<0>();
+          epi_barrier();
+        }
         for (int c0 = 0; c0 < Cw; c0 += 32) {
           tmem_ld32(trow + c0, v);
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
-            float o4[4];
+            if (c0 + j < Cw) {
+              float4* sp = reinterpret_cast<float4*>(stg + row * pitch + c0 + j);
+              float4 acc4 = res_in_stage ? *sp : make_float4(0.f, 0.f, 0.f, 0.f);
+              float o4[4] = {acc4.x, acc4.y, acc4.z, acc4.w};
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int n = c0 + j + e;
-              o4[e] = (n < a.N) ? apply_act(__uint_as_float(v[j + e]) + s_bias[n], a.act, a.slope) : 0.f;
+              for (int e = 0; e < 4; ++e) o4[e] += apply_act(__uint_as_float(v[j + e]) + s_bias[c0 + j + e], a.act, a.slope);
+              *sp = make_float4(o4[0], o4[1], o4[2], o4[3]);
             }
-            if (c0 + j < pitch) *reinterpret_cast<float4*>(stg + row * pitch + c0 + j) = make_float4(o4[0], o4[1], o4[2], o4[3]);
           }
         }
       }
@@ -307,16 +318,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const bool col_real = c4 < C4, col_any = c4 < P4;
         for (int rb = 0; rb < 32; rb += RB) {  // this warp's rows: ew, ew + 4, ...
           long long tok[RB];
-          float4 rr[RB], gg[RB];
+          float4 gg[RB];
           uint2 cy[RB];
 #pragma unroll
           for (int i = 0; i < RB; ++i) {
             tok[i] = s_tok[ew + 4 * (rb + i)];
-            rr[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            gg[i] = rr[i];
+            gg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
             cy[i] = make_uint2(0u, 0u);
             if (tok[i] >= 0 && col_real) {
-              if (a.res_f32) rr[i] = __ldg(reinterpret_cast<const float4*>(a.res_f32 + tok[i] * a.ldr + c4 * 4));
               if (has_cab) {
                 cy[i] = __ldg(reinterpret_cast<const uint2*>(caby + tok[i] * a.ld_caby + c4 * 4));
                 gg[i] = __ldg(reinterpret_cast<const float4*>(a.cab_gate + (long long)s_img[ew + 4 * (rb + i)] * Cw + c4 * 4));
@@ -329,7 +338,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
             if (col_real) {
               val = *reinterpret_cast<const float4*>(stg + (ew + 4 * (rb + i)) * pitch + c4 * 4);
-              val.x += rr[i].x, val.y += rr[i].y, val.z += rr[i].z, val.w += rr[i].w;
               if (has_cab) {
                 const float2 c01 = unpack16(cy[i].x, fmt), c23 = unpack16(cy[i].y, fmt);
                 val.x = fmaf(c01.x, gg[i].x, val.x), val.y = fmaf(c01.y, gg[i].y, val.y);
