@@ -100,3 +100,22 @@ def test_tables_match_oracle(pkg, oracle):
     tim = oracle.table_index_mask(cfg, (128, 128))
     for k in ("table_w", "table_sh", "table_sv"):
         assert torch.equal(getattr(m, k), tim[k])
+
+
+def test_reference_checkpoint_ingestion(pkg, oracle, tmp_path):
+    """tools/trainer.py:93-115: Lightning checkpoint with `model.`-prefixed keys, engine buffers and the reference's
+    table / index / mask buffers -> strict load."""
+    from grl_image_restoration_b200 import checkpoint
+
+    cfg = pkg.configs.micro_config()
+    sd = oracle.synth_state_dict(cfg, seed=4)
+    full = {"model." + k: v for k, v in sd.items()}
+    full.update({"model." + k: v for k, v in oracle.table_index_mask(cfg, (32, 32)).items()})
+    full.update(current_val_metric=torch.tensor(0.0), best_val_metric=torch.tensor(31.2), best_iter=torch.tensor(5))
+    path = tmp_path / "last.ckpt"
+    torch.save({"state_dict": full, "epoch": 3}, path)
+    m = pkg.GRL(**cfg)
+    res = checkpoint.load_reference_checkpoint(m, str(path))
+    assert not res.missing_keys and not res.unexpected_keys
+    for k, v in sd.items():
+        assert torch.equal(m.state_dict()[k], v)

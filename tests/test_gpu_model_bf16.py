@@ -36,7 +36,8 @@ def test_block_and_stage_bf16_vs_reference_taps(pkg, oracle, cases, golden_loade
 
 @pytest.mark.parametrize("precision", ["fp16", "bf16"])
 @pytest.mark.parametrize("variant,task,scale,size,hw", [("tiny", "sr", 2, 64, (64, 64)), ("small", "sr", 4, 64, (64, 64)),
-                                                        ("base", "sr", 4, 64, (64, 64)), ("small", "dn", 1, 128, (100, 120))])
+                                                        ("base", "sr", 4, 64, (64, 64)), ("small", "dn", 1, 128, (100, 120)),
+                                                        ("tiny", "deblur", 1, 96, (96, 96))])
 def test_psnr_gate_vs_oracle(pkg, oracle, device, variant, task, scale, size, hw, precision):
     """Weights drawn like the reference's constructor does (style "init"): the realistic sensitivity regime.
     fp16 operands must meet the 0.01 dB gate with PSNR(cand, ref) >= 56 dB; bf16 operands are
