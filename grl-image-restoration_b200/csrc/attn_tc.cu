@@ -240,6 +240,10 @@ __global__ void __launch_bounds__(kAttnThreads, (KT <= 32 ? 4 : KT <= 64 ? 3 : 2
     const int base_i = (tq.ih + a.gk.wh - 1) * Wt + tq.iw + a.gk.ww - 1;
     const int q_rid = region_id(a.gq, tq.r, tq.c);
     const bool need_mask = a.use_mask && (wr == nwh - 1 || wc == nww - 1);
+    // ones-column: when head_dim < 32 the projection epilogue sets column 31 of every V row to 1, so O[:, 31] =
+    // sum_j P_ij is the softmax denominator -- accumulated by the tensor core from the very P it multiplies with V,
+    // and rescaled together with the other columns; the 64 FADDs per tile of the explicit row sum disappear.
+    const bool ones = a.ones_col != 0;
 
     float o[kDP];
 #pragma unroll
@@ -315,7 +319,7 @@ __global__ void __launch_bounds__(kAttnThreads, (KT <= 32 ? 4 : KT <= 64 ? 3 : 2
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
           p[e] = ex2(lg[c * 8 + e] - m_new);
-          ps[e & 3] += p[e];
+          if (!ones) ps[e & 3] += p[e];
         }
         uint4 pk;
         if (fmt == FMT_BF16)
@@ -355,7 +359,7 @@ __global__ void __launch_bounds__(kAttnThreads, (KT <= 32 ? 4 : KT <= 64 ? 3 : 2
       for (int e = 0; e < kDP; ++e) o[e] += __uint_as_float(v[e]);
     }
     if (q_ok) {
-      const float inv = 1.0f / l_run;
+      const float inv = 1.0f / (ones ? o[kDP - 1] : l_run);
       __nv_bfloat16* dst = a.o_dense ? a.out + (((long long)bw * a.heads + h) * Nq + qi) * kDP
                                      : a.out + q_tok * a.ldo + a.o_off + h * kDP;
 #pragma unroll

@@ -391,7 +391,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             ss = fmaf(o[j], o[j], ss);
           }
           const float sc = __ldg(a.slot_scale + slot);
-          const float mul = sc > 0.f ? sc / fmaxf(sqrtf(ss), 1e-12f) : 1.0f;  // scale <= 0 marks a value slot
+          // x / max(||x||, 1e-12) == x * rsqrt(max(||x||^2, 1e-24));  scale <= 0 marks a value slot
+          const float mul = sc > 0.f ? sc * rsqrtf(fmaxf(ss, 1e-24f)) : 1.0f;
 #pragma unroll
           for (int j = 0; j < 32; ++j) o[j] *= mul;
         } else {

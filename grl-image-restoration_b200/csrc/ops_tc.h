@@ -75,6 +75,7 @@ struct AttnTcArgs {
   const float* bias;  // (heads, 4, rows_pad) fp32, log2 domain: copy c holds the table shifted right by c entries
   int rows, rows_pad;
   int use_mask;
+  int ones_col;  // V[:, 31] == 1 for every key: take the softmax denominator from O[:, 31]
 };
 int launch_attn_tc(const AttnTcArgs& a, cudaStream_t st);
 

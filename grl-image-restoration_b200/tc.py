@@ -122,7 +122,7 @@ def gemm(x16, w16, bias, *, M=0, image=None, kpad, npad, taps=1, epi=EPI_BIAS_AC
 
 
 def attention(gq, gk, q, q_off, k, k_off, v, v_off, out, o_off, B, heads, bias, use_mask, v_dense=False,
-              o_dense=False, tag="attn"):
+              o_dense=False, tag="attn", ones_col=False):
     p = capi.GrlTcAttn()
     p.fmt = fmt_of(q)
     p.gq, p.gk = gq, gk
@@ -134,6 +134,7 @@ def attention(gq, gk, q, q_off, k, k_off, v, v_off, out, o_off, B, heads, bias, 
         raise RuntimeError("grl_b200: attention bias must be the (heads, 4, rows_pad) table of bias_table_log2 / shifted_copies")
     p.B, p.heads, p.bias, p.use_mask = B, heads, bias.data_ptr(), int(use_mask)
     p.rows, p.rows_pad = (gq.wh + gk.wh - 1) * (gq.ww + gk.ww - 1), bias.shape[2]
+    p.ones_col = int(ones_col)
     K._timed(tag, lambda: capi.check(capi.lib().grl_tc_attn(ctypes.byref(p), capi.stream())))
 
 
@@ -200,6 +201,15 @@ class BlockPlan:
         self.n_qkv = self.nslots * SLOT
         self.w_qkv = _pad_matrix(at.qkv.body.weight, self.n_qkv, self.cpad, row_map=rmap, fmt=fmt)
         self.b_qkv = _pad_vector(at.qkv.body.bias if at.qkv.body.bias is not None else torch.zeros(3 * C, device=at.qkv.body.weight.device), self.n_qkv, rmap)
+        # ones-column (attn_tc.cu): with head_dim < 32 the last slot column of every VALUE slot is 1 (set through the
+        # bias; its weight row is zero), so the P V MMA also produces the softmax denominator.  The stripe pass-1 output
+        # X1 inherits it (O[:, 31] / O[:, 31] == 1) and is the value operand of pass 2.
+        self.ones_w, self.ones_s = dw < SLOT, ds < SLOT
+        for half, (hh, on) in enumerate(((hw, self.ones_w), (hs, self.ones_s))):
+            if on:
+                base = (0 if half == 0 else 3 * hw) + 2 * hh
+                for head in range(hh):
+                    self.b_qkv[(base + head) * SLOT + SLOT - 1] = 1.0
         # --- anchor projection: dest row = head*32 + e
         amap = [head * SLOT + e for head in range(hs) for e in range(ds)]
         red = at.anchor.body[0].reduction
@@ -278,15 +288,15 @@ class BlockPlan:
         s = wa.shift_size
         gw = G.token_grid(x_size, wa.window_size, (s, s))
         attention(gw, gw, qkv, 0, qkv, hw * SLOT, qkv, 2 * hw * SLOT, merged, 0, B, hw, bias_w, t["mask_w"] is not None,
-                  tag="window_attn")
+                  tag="window_attn", ones_col=self.ones_w)
         tok, anc = sa.grids(x_size)
         nW = (tok.H // tok.wh) * (tok.W // tok.ww)
         x1 = _h16(B * nW * hs * anc.wh * anc.ww, SLOT, device=dev, fmt=fmt)
         use_mask = t["mask_a2w"] is not None
         attention(anc, tok, anchor, 0, qkv, (3 * hw + hs) * SLOT, qkv, (3 * hw + 2 * hs) * SLOT, x1, 0, B, hs, bias_1,
-                  use_mask, o_dense=True, tag="stripe_attn")
+                  use_mask, o_dense=True, tag="stripe_attn", ones_col=self.ones_s)
         attention(tok, anc, qkv, 3 * hw * SLOT, anchor, 0, x1, 0, merged, hw * SLOT, B, hs, bias_2, use_mask,
-                  v_dense=True, tag="stripe_attn")
+                  v_dense=True, tag="stripe_attn", ones_col=self.ones_s)
         # CAB
         cab_y = gate = None
         if self.cab:

@@ -215,6 +215,7 @@ typedef struct {
   int32_t rows;
   int32_t rows_pad;
   int32_t use_mask;
+  int32_t ones_col; /* 1: column 31 of every V row is 1.0 (head_dim < 32) -> the row sum comes out of the P V MMA */
 } GrlTcAttn;
 int grl_tc_attn(const GrlTcAttn* p, void* stream);
 

@@ -214,3 +214,32 @@ def test_attention_tc_stripe_chain(tc, oracle, device, B, H, W, stripe, df, head
     assert (x1d.cpu().float().view(x1.shape) - x1).abs().max().item() <= 4e-2 * max(1.0, x1.abs().max().item())
     err = (got - ref).abs().max().item()
     assert err <= 5e-2 * max(1.0, ref.abs().max().item()), err
+
+
+def test_attention_tc_ones_column_denominator(tc, oracle, device):
+    """head_dim < 32: V[:, 31] == 1 makes the P V MMA produce the softmax denominator (ones_col=True)."""
+    from grl_image_restoration_b200 import geometry as G
+
+    B, H, W, ws, heads, d = 1, 32, 64, (32, 32), 3, 30
+    nsl, L = 3 * heads, H * W
+    g = torch.Generator().manual_seed(77)
+    qkv = torch.zeros(B, L, nsl, 32)
+    qkv[..., :d] = torch.randn(B, L, nsl, d, generator=g)
+    qkv[:, :, : 2 * heads, :d] = F.normalize(qkv[:, :, : 2 * heads, :d], dim=-1)
+    qkv[:, :, :heads] *= 9.0
+    table = torch.rand(heads, (2 * ws[0] - 1) * (2 * ws[1] - 1), generator=g) * 16 * tc.LOG2E
+    s = ws[0] // 2
+    t = torch.roll(qkv.view(B, H, W, nsl * 32), (-s, -s), (1, 2))
+    win = oracle.partition(t, ws).reshape(-1, ws[0] * ws[1], 3, heads, 32).permute(2, 0, 3, 1, 4)
+    o = _attn_ref(win[0], win[1], win[2], oracle.position_index(list(ws)), table, oracle.shift_mask([H, W], list(ws), [s, s]))
+    ref = torch.roll(oracle.unpartition(o.transpose(1, 2).reshape(-1, ws[0], ws[1], heads * 32), ws, (H, W)), (s, s), (1, 2))
+    ref = ref.reshape(B, L, heads, 32)
+    qkv[:, :, 2 * heads:, 31] = 1.0  # what the QKV epilogue writes through the bias when head_dim < 32
+    q16 = qkv.view(B * L, nsl * 32).to(device).to(torch.float16)
+    out = torch.zeros(B * L, heads * 32, device=device, dtype=torch.float16)
+    grid = G.token_grid((H, W), ws, (s, s))
+    tc.attention(grid, grid, q16, 0, q16, heads * 32, q16, 2 * heads * 32, out, 0, B, heads,
+                 tc.shifted_copies(table.to(device)), True, ones_col=True)
+    got = out.cpu().float().view(B, L, heads, 32)
+    assert (got[..., :d] - ref[..., :d]).abs().max().item() <= 4e-2 * max(1.0, ref.abs().max().item())
+    assert (got[..., 31] - 1.0).abs().max().item() <= 2e-3 and got[..., 30].abs().max().item() == 0
