@@ -15,7 +15,7 @@ struct GemmTcArgs {
   int fmt;  // operand / 16-bit activation format: 0 = fp16, 1 = bf16
   // filled by launch_gemm_tc
   long long M;
-  int nk, taps;
+  int nk, taps, n_tiles;
   int H, W, tiles_x, tiles_y;
   int epi_mode;  // 0 = 16-bit staging, 1 = fp32 staging, 2 = direct
   // epilogue

@@ -42,8 +42,13 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   int spins = 0;
+  long long t0 = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > 4000) __trap();  // 4000 x ~1 ms suspend windows
+    if ((++spins & 63) == 0) {  // wall-clock bound (~2 s), checked rarely so that waiting costs no issue slots
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000ll) __trap();
+    }
   }
 }
 
