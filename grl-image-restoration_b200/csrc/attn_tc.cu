@@ -59,11 +59,13 @@ constexpr int kAttnThreads = kQT + 32;  // 4 softmax warps (one query row per th
 //       QK(t+1) as soon as every softmax thread has pulled S_t out of TMEM (s_free), PV(t) as soon as P_t is in smem
 //       and O_{t-1} has been consumed (p_full); completion is signalled by tcgen05.commit on bar_s / bar_o.
 //   warps 0-3 (softmax, thread = query row = TMEM lane): wait bar_s(t) -> S_t + bias -> registers -> arrive s_free ->
-//       exp2 / running max / bf16|fp16 P_t -> smem -> wait bar_o(t-1), o = (o + O_{t-1}) * corr_t -> arrive p_full.
+//       exp2 / running max / bf16|fp16 P_t -> smem -> wait bar_o(t-1), o = o * corr_{t-1} + O_{t-1} -> arrive p_full.
 // The only waits of a softmax warp are on MMA completions.
 // KW: key-window width when it is a power of two >= 8 (bias rows read as aligned float4 from the 4-way shifted table
 // copies), 0 = generic scalar path.
-template <int KT, int KW>
+// VAR: bit 0 = bf16 operands (else fp16), bit 1 = ones-column denominators -- compile-time so the exp / pack loop has no
+// uniform branches (they were ~9 % of the softmax warps' issue slots).
+template <int KT, int KW, int VAR>
 __global__ void __launch_bounds__(kAttnThreads, (KT <= 32 ? 4 : KT <= 64 ? 3 : 2)) attn_tc_kernel(const AttnTcArgs a) {
   static_assert(KT == 32 || KT == 64 || KT == 128, "P tiles: 64-byte rows (SWIZZLE_64B) or 128-byte rows (SWIZZLE_128B)");
   extern __shared__ uint8_t smem_raw[];
@@ -112,7 +114,7 @@ __global__ void __launch_bounds__(kAttnThreads, (KT <= 32 ? 4 : KT <= 64 ? 3 : 2
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const int fmt = a.fmt;
+  constexpr int fmt = (VAR & 1) ? FMT_BF16 : FMT_F16;
 
   if (warp == 4) {
     // =============================================================== producer + MMA issuer
@@ -243,12 +245,13 @@ __global__ void __launch_bounds__(kAttnThreads, (KT <= 32 ? 4 : KT <= 64 ? 3 : 2
     // ones-column: when head_dim < 32 the projection epilogue sets column 31 of every V row to 1, so O[:, 31] =
     // sum_j P_ij is the softmax denominator -- accumulated by the tensor core from the very P it multiplies with V,
     // and rescaled together with the other columns; the 64 FADDs per tile of the explicit row sum disappear.
-    const bool ones = a.ones_col != 0;
+    constexpr bool ones = (VAR & 2) != 0;
 
     float o[kDP];
 #pragma unroll
     for (int e = 0; e < kDP; ++e) o[e] = 0.f;
     float m_run = -INFINITY, l_run = 0.f;
+    float corr_prev = 0.f;  // exp2(m_{t-2} - m_{t-1}): brings o (relative to m_{t-2}) to the reference of O_{t-1}
 
     for (int t = 0; t < ntiles; ++t) {
       const int buf = t & 1, k0 = t * KT, slot = t % 3;
@@ -335,7 +338,8 @@ __global__ void __launch_bounds__(kAttnThreads, (KT <= 32 ? 4 : KT <= 64 ? 3 : 2
       }
       l_run = l_run * corr + ((ps[0] + ps[1]) + (ps[2] + ps[3]));
 
-      // ---- fold in the previous tile's P V (it has had a whole softmax to finish) and rescale
+      // ---- fold in the previous tile's P V (it has had a whole softmax to finish).  o is kept relative to the running
+      // max at which the last folded O was computed, so the fold is one FFMA per element: o <- o * corr_{t-1} + O_{t-1}
       if (t > 0) {
         mbar_wait(bar_o, (t - 1) & 1);
         tcgen05_fence_after();
@@ -343,8 +347,9 @@ __global__ void __launch_bounds__(kAttnThreads, (KT <= 32 ? 4 : KT <= 64 ? 3 : 2
         tmem_ld32(trow + KT, v);
         tmem_ld_wait();
 #pragma unroll
-        for (int e = 0; e < kDP; ++e) o[e] = (o[e] + __uint_as_float(v[e])) * corr;
+        for (int e = 0; e < kDP; ++e) o[e] = fmaf(o[e], corr_prev, __uint_as_float(v[e]));
       }
+      corr_prev = corr;
       tcgen05_fence_before();
       fence_proxy_async_smem();  // P_t (generic-proxy stores) -> visible to the tensor core
       mbar_arrive(p_full);
@@ -356,7 +361,7 @@ __global__ void __launch_bounds__(kAttnThreads, (KT <= 32 ? 4 : KT <= 64 ? 3 : 2
       tmem_ld32(trow + KT, v);
       tmem_ld_wait();
 #pragma unroll
-      for (int e = 0; e < kDP; ++e) o[e] += __uint_as_float(v[e]);
+      for (int e = 0; e < kDP; ++e) o[e] = fmaf(o[e], corr_prev, __uint_as_float(v[e]));  // now relative to the final max
     }
     if (q_ok) {
       const float inv = 1.0f / (ones ? o[kDP - 1] : l_run);
@@ -377,9 +382,9 @@ __global__ void __launch_bounds__(kAttnThreads, (KT <= 32 ? 4 : KT <= 64 ? 3 : 2
   }
 }
 
-template <int KT, int KW>
-static int launch_attn_one(const AttnTcArgs& a, unsigned nblk, cudaStream_t st) {
-  auto kern = attn_tc_kernel<KT, KW>;
+template <int KT, int KW, int VAR>
+static int launch_attn_var(const AttnTcArgs& a, unsigned nblk, cudaStream_t st) {
+  auto kern = attn_tc_kernel<KT, KW, VAR>;
   static bool configured = false;
   if (!configured) {
     GRL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnSmem<KT>::TOTAL));
@@ -388,6 +393,16 @@ static int launch_attn_one(const AttnTcArgs& a, unsigned nblk, cudaStream_t st) 
   kern<<<nblk, kAttnThreads, AttnSmem<KT>::TOTAL, st>>>(a);
   GRL_LAUNCH_CHECK("attn_tc_kernel");
   return GRL_OK;
+}
+
+template <int KT, int KW>
+static int launch_attn_one(const AttnTcArgs& a, unsigned nblk, cudaStream_t st) {
+  switch ((a.fmt == FMT_BF16 ? 1 : 0) | (a.ones_col ? 2 : 0)) {
+    case 0: return launch_attn_var<KT, KW, 0>(a, nblk, st);
+    case 1: return launch_attn_var<KT, KW, 1>(a, nblk, st);
+    case 2: return launch_attn_var<KT, KW, 2>(a, nblk, st);
+    default: return launch_attn_var<KT, KW, 3>(a, nblk, st);
+  }
 }
 
 int launch_attn_tc(const AttnTcArgs& a, cudaStream_t st) {
@@ -403,28 +418,15 @@ int launch_attn_tc(const AttnTcArgs& a, cudaStream_t st) {
   const int Nq = a.gq.wh * a.gq.ww;
   const long long nblk = (long long)a.B * (a.gq.H / a.gq.wh) * (a.gq.W / a.gq.ww) * a.heads * ceil_div(Nq, kQT);
   GRL_REQUIRE(nblk < (1ll << 31), "attn_tc: grid too large");
-  static int kt = 0;  // keys per tile: 64 (3 CTAs / SM) or 128 via GRL_ATTN_KT=128 (2 CTAs / SM, half the hand-offs)
-  if (kt == 0) {
-    const char* e = getenv("GRL_ATTN_KT");
-    kt = (e && atoi(e) == 128) ? 128 : (e && atoi(e) == 32) ? 32 : 64;
+  // 64 keys per tile, 3 CTAs / SM (32- and 128-key tiles were measured slower: profiles/r1_tc_path_final.md)
+  switch (a.gk.ww) {
+    case 8: return launch_attn_one<64, 8>(a, (unsigned)nblk, st);
+    case 16: return launch_attn_one<64, 16>(a, (unsigned)nblk, st);
+    case 32: return launch_attn_one<64, 32>(a, (unsigned)nblk, st);
+    case 64: return launch_attn_one<64, 64>(a, (unsigned)nblk, st);
+    case 128: return launch_attn_one<64, 128>(a, (unsigned)nblk, st);
+    default: return launch_attn_one<64, 0>(a, (unsigned)nblk, st);
   }
-#define GRL_ATTN_DISPATCH(KTV)                                         \
-  switch (a.gk.ww) {                                                    \
-    case 8: return launch_attn_one<KTV, 8>(a, (unsigned)nblk, st);      \
-    case 16: return launch_attn_one<KTV, 16>(a, (unsigned)nblk, st);    \
-    case 32: return launch_attn_one<KTV, 32>(a, (unsigned)nblk, st);    \
-    case 64: return launch_attn_one<KTV, 64>(a, (unsigned)nblk, st);    \
-    case 128: return launch_attn_one<KTV, 128>(a, (unsigned)nblk, st);  \
-    default: return launch_attn_one<KTV, 0>(a, (unsigned)nblk, st);     \
-  }
-  if (kt == 128) {
-    GRL_ATTN_DISPATCH(128)
-  }
-  if (kt == 32) {
-    GRL_ATTN_DISPATCH(32)
-  }
-  GRL_ATTN_DISPATCH(64)
-#undef GRL_ATTN_DISPATCH
 }
 
 }  // namespace tc
