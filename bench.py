@@ -21,9 +21,17 @@ import torch
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-# keep stdout to the single JSON line: NCCL prints its version banner to stdout at NCCL_DEBUG=VERSION
-if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-    os.environ["NCCL_DEBUG"] = "WARN"
+# keep stdout to the single JSON line: libraries below us (NCCL's version banner, for one) write to file descriptor 1.
+# Everything that is not the result line goes to stderr; the result line goes to the saved real stdout.
+sys.stdout.flush()
+RESULT_OUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
+
+def emit(result):
+    RESULT_OUT.write(json.dumps(result) + "\n")
+    RESULT_OUT.flush()
+
 
 WORKLOADS = {
     # name: (variant, task, scale, tile, tiles per GPU)
@@ -154,14 +162,14 @@ def main():
         if rank != 0:
             return
         r = cpu_leg(WORKLOADS[a.workload], max(a.steps, 1), W)
-        print(json.dumps({
+        emit({
             "impl": "reference", "metric": metric, "value": r["value"], "unit": "Mpix/s", "n_gpus": a.gpus,
             "steps": a.steps, "warmup": W, "ms_per_step": r["sec_per_step"] * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg_desc,
             "cpu_baseline": {"value": r["value"], "unit": "Mpix/s", "cores": r["cores"], "kind": "port",
                              "sample": r["sample"]},
             "e2e": {"value": r["value"], "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        }))
+        })
         return
 
     # ------------------------------------------------------------------ our arm
@@ -274,8 +282,8 @@ def main():
             "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tflops"],
             "peak_source": f"bf16 sustained, {pk['src']}", "traffic": traffic,
             "traffic_note": "average DRAM bytes per attention launch from profiles/traffic.json (one ncu --set full capture)",
-            "co_bound": "softmax: 16 MUFU ex2/clk/SM and ~12 SIMT instructions per score element cap this kernel at "
-                        "~25 % of the tensor pipe at head_dim 32 (DESIGN.md section 5)",
+            "co_bound": "softmax: one ex2 per 128 MMA FLOP at head_dim 32 -- 16 MUFU/clk/SM cap this kernel at 41 % of "
+                        "the tensor peak, ~6 SIMT instructions per score element lower (DESIGN.md section 5.3)",
             "share_of_step": attn_total_ms / ms_total, "launches_timed": attn_launches,
             "algorithmic_gflop_per_image": counts["f_attn"] / 1e9, "qk_frac": achieved / 2 / pk["tflops"],
             "whole_model_tflops": None}
@@ -309,7 +317,7 @@ def main():
                          "psnr_cand_vs_reference_db": orc.psnr(yc, r["y"], b).mean().item(),
                          "delta_psnr_vs_gt_db": abs(orc.psnr(yc, gt, b).mean().item() - orc.psnr(r["y"], gt, b).mean().item()),
                          "sample": f"one {CPU_SAMPLE_TILE}x{CPU_SAMPLE_TILE} tile, same weights, reference CPU path"}
-    print(json.dumps(out))
+    emit(out)
     if world > 1:
         dist.destroy_process_group()
 
