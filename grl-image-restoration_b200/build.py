@@ -46,7 +46,7 @@ def build(force=False, verbose=False):
                             for h in glob.glob(os.path.join(CSRC, "*.h")) + glob.glob(os.path.join(CSRC, "*.cuh"))
                             + [os.path.join(os.path.dirname(PKG), "include", "grl_b200.h")])):
             continue
-        cmd = [nvcc] + NVCC_FLAGS + ["-c", src, "-o", obj]
+        cmd = [nvcc] + NVCC_FLAGS + os.environ.get("GRL_NVCC_DEFINES", "").split() + ["-c", src, "-o", obj]  # A/B builds
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     for src, p in procs:
         out, _ = p.communicate()
