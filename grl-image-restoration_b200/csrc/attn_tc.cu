@@ -20,37 +20,11 @@
 #include "grl_common.cuh"
 #include "ops_f32.h"
 #include "ops_tc.h"
+#include "attn_tc.cuh"
 #include "tc_common.cuh"
 
 namespace grl {
 namespace tc {
-
-constexpr int kQT = 128;
-constexpr int kDP = 32;  // padded head dim (slot width)
-constexpr float kMaskLog2 = -100.0f * 1.4426950408889634f;
-
-__device__ __forceinline__ float ex2(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-
-// byte offset of 16-byte chunk c of row r in a 64-byte-row SWIZZLE_64B tile
-__device__ __forceinline__ uint32_t sw64(int r, int c) { return (uint32_t)(r * 64 + ((c ^ ((r >> 1) & 3)) << 4)); }
-
-template <int KT>
-struct AttnSmem {
-  static constexpr int Q_BYTES = kQT * 64;
-  static constexpr int KV_BYTES = KT * 64;
-  static constexpr int P_BYTES = kQT * KT * 2;
-  static constexpr int OFF_K = Q_BYTES;
-  static constexpr int OFF_V = OFF_K + 2 * KV_BYTES;
-  static constexpr int OFF_P = (OFF_V + 2 * KV_BYTES + 1023) / 1024 * 1024;  // two P buffers
-  static constexpr int OFF_META = OFF_P + 2 * P_BYTES;                       // int koff[3][KT], rid[3][KT] (tile % 3)
-  static constexpr int OFF_BAR = OFF_META + 6 * KT * 4;
-  static constexpr int TOTAL = OFF_BAR + 128 + 1024;
-  static_assert(P_BYTES % 1024 == 0, "P tiles must be 1024-byte aligned");
-};
 
 constexpr int kAttnThreads = kQT + 32;  // 4 softmax warps (one query row per thread) + 1 producer / MMA warp
 
@@ -405,6 +379,18 @@ static int launch_attn_one(const AttnTcArgs& a, unsigned nblk, cudaStream_t st) 
   }
 }
 
+int attn_variant(int set) {
+  static int variant = -1;
+  if (variant < 0) {
+    const char* e = getenv("GRL_ATTN_SPLIT");
+    const int v = e ? atoi(e) : 0;
+    variant = (v == 1 || v == 2) ? v : 0;
+  }
+  const int prev = variant;
+  if (set >= 0 && set <= 2) variant = set;
+  return prev;
+}
+
 int launch_attn_tc(const AttnTcArgs& a, cudaStream_t st) {
   if (a.B == 0) return GRL_OK;
   int rc;
@@ -418,6 +404,8 @@ int launch_attn_tc(const AttnTcArgs& a, cudaStream_t st) {
   const int Nq = a.gq.wh * a.gq.ww;
   const long long nblk = (long long)a.B * (a.gq.H / a.gq.wh) * (a.gq.W / a.gq.ww) * a.heads * ceil_div(Nq, kQT);
   GRL_REQUIRE(nblk < (1ll << 31), "attn_tc: grid too large");
+  const int split = attn_variant(-1);  // 1 | 2: experimental two-threads-per-row kernel (attn_tc_split.cu), default 0
+  if (split == 1 || split == 2) return launch_attn_tc_split(a, (unsigned)nblk, split, st);
   // 64 keys per tile, 3 CTAs / SM (32- and 128-key tiles were measured slower: profiles/r1_tc_path_final.md)
   switch (a.gk.ww) {
     case 8: return launch_attn_one<64, 8>(a, (unsigned)nblk, st);

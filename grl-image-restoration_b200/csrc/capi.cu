@@ -288,4 +288,6 @@ int grl_tc_attn(const GrlTcAttn* p, void* stream) {
   return tc::launch_attn_tc(a, (cudaStream_t)stream);
 }
 
+int grl_tc_attn_variant(int variant) { return tc::attn_variant(variant); }
+
 }  // extern "C"

@@ -78,6 +78,9 @@ struct AttnTcArgs {
   int ones_col;  // V[:, 31] == 1 for every key: take the softmax denominator from O[:, 31]
 };
 int launch_attn_tc(const AttnTcArgs& a, cudaStream_t st);
+// experimental two-threads-per-row variant (attn_tc_split.cu); reached through launch_attn_tc when the variant is 1|2
+int attn_variant(int set);  // -1 (or anything outside {0,1,2}): query only; returns the previous value
+int launch_attn_tc_split(const AttnTcArgs& a, unsigned nblk, int mode, cudaStream_t st);
 
 }  // namespace tc
 }  // namespace grl

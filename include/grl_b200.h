@@ -219,6 +219,11 @@ typedef struct {
 } GrlTcAttn;
 int grl_tc_attn(const GrlTcAttn* p, void* stream);
 
+/* Kernel variant behind grl_tc_attn: 0 = one thread per query row (default), 1 / 2 = EXPERIMENTAL two threads per row
+ * at 2 / 3 CTAs per SM (attn_tc_split.cu).  Initial value: environment variable GRL_ATTN_SPLIT (unset = 0).  Returns the
+ * previous value; a value outside {0, 1, 2} only queries.  Same results contract as variant 0. */
+int grl_tc_attn_variant(int variant);
+
 #ifdef __cplusplus
 }
 #endif

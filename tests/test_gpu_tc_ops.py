@@ -3,6 +3,7 @@ the same bf16-rounded operands.  Tolerances are bf16-sized: these tests prove de
 correctness (a wrong swizzle or index gives O(1) errors), the PSNR gate of the whole network is in
 test_gpu_model_bf16.py."""
 import math
+import os
 
 import pytest
 import torch
@@ -20,13 +21,21 @@ def bf(t, fmt=0):
     return t.to(torch.bfloat16 if fmt else torch.float16).float()
 
 
-@pytest.fixture(scope="module")
-def tc(pkg, device):
+# Attention kernel variants (grl_tc_attn_variant): 0 = production.  The experimental two-threads-per-row kernels (1, 2)
+# are exercised by the same tests only on request -- GRL_TEST_EXPERIMENTAL=1 -- because a faulting experimental kernel
+# would poison the CUDA context of the whole pytest process.
+ATTN_VARIANTS = [0, 1, 2] if os.environ.get("GRL_TEST_EXPERIMENTAL") == "1" else [0]
+
+
+@pytest.fixture(scope="module", params=ATTN_VARIANTS, ids=lambda v: f"attn{v}")
+def tc(pkg, device, request):
     from grl_image_restoration_b200 import capi, tc as T
 
     if capi.lib().grl_device_ok() != 1:
         pytest.skip("tcgen05 path needs sm_100")
-    return T
+    prev = capi.lib().grl_tc_attn_variant(request.param)
+    yield T
+    capi.lib().grl_tc_attn_variant(prev)
 
 
 @pytest.mark.parametrize("fmt", [0, 1])

@@ -19,6 +19,7 @@ ap.add_argument("--batch", type=int, default=1)
 ap.add_argument("--iters", type=int, default=3)
 ap.add_argument("--precision", default=None)
 ap.add_argument("--style", default="spread")
+ap.add_argument("--attn-variants", default="0", help="comma list of grl_tc_attn_variant values to time in turn (A/B in one process)")
 a = ap.parse_args()
 pkg = load_package()
 import grl_oracle as orc  # noqa: E402  (weights only)
@@ -30,16 +31,23 @@ m = m.cuda().eval()
 if a.precision is not None and hasattr(m, "set_precision"):
     m.set_precision(a.precision)
 x = torch.rand(a.batch, 3, a.size, a.size, device="cuda")
-m(x)
-torch.cuda.synchronize()
-ts = []
-for _ in range(a.iters):
-    e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
-    e0.record()
-    y = m(x)
-    e1.record()
+from grl_image_restoration_b200 import capi  # noqa: E402
+
+for variant in [int(v) for v in a.attn_variants.split(",")]:
+    capi.lib().grl_tc_attn_variant(variant)
+    y0 = m(x)
     torch.cuda.synchronize()
-    ts.append(e0.elapsed_time(e1))
-ms = sorted(ts)[len(ts) // 2]
-print(f"{a.variant}/{a.task} x{a.scale} {a.size}^2 B={a.batch} prec={a.precision}: {ms:.1f} ms/forward, "
-      f"{a.batch * a.size * a.size / 1e6 / (ms / 1e3):.4f} Mpix/s, peak mem {torch.cuda.max_memory_allocated() / 2**30:.2f} GiB")
+    if variant == int(a.attn_variants.split(",")[0]):
+        y_first = y0
+    ts = []
+    for _ in range(a.iters):
+        e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+        e0.record()
+        y = m(x)
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ms = sorted(ts)[len(ts) // 2]
+    print(f"{a.variant}/{a.task} x{a.scale} {a.size}^2 B={a.batch} prec={a.precision} attn_variant={variant}: {ms:.1f} ms/forward, "
+          f"{a.batch * a.size * a.size / 1e6 / (ms / 1e3):.4f} Mpix/s, peak mem {torch.cuda.max_memory_allocated() / 2**30:.2f} GiB, "
+          f"max |y - y(first variant)| = {(y0 - y_first).abs().max().item():.3e}")
