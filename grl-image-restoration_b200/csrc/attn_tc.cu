@@ -26,6 +26,40 @@
 namespace grl {
 namespace tc {
 
+// ---- differential-timing builds (tools/attn_diag.py): each GRL_ATTN_DIAG_* define removes ONE ingredient of the kernel
+// so that its cost shows up as a time difference.  The results of such a build are WRONG by construction; nothing but
+// tools/attn_diag.py defines these, and the default build is bit-for-bit the production kernel.
+#ifdef GRL_ATTN_DIAG_NOBIAS  // no bias-table loads (logits = S)
+#define GRL_DIAG_BIAS(ptr) make_float4(0.f, 0.f, 0.f, 0.f)
+#else
+#define GRL_DIAG_BIAS(ptr) __ldg(ptr)
+#endif
+#ifdef GRL_ATTN_DIAG_NOEXP  // no MUFU (P = logit - max, garbage but finite)
+#define GRL_DIAG_EX2(x) (x)
+#else
+#define GRL_DIAG_EX2(x) ex2(x)
+#endif
+#ifdef GRL_ATTN_DIAG_NOPSTORE  // P never written to shared memory
+#define GRL_DIAG_PSTORE(stmt)
+#else
+#define GRL_DIAG_PSTORE(stmt) stmt
+#endif
+#ifdef GRL_ATTN_DIAG_NOFOLD  // O_{t-1} never read back from TMEM inside the loop (the wait on bar_o stays)
+#define GRL_DIAG_FOLD(block)
+#else
+#define GRL_DIAG_FOLD(block) block
+#endif
+#ifdef GRL_ATTN_DIAG_NOPFENCE  // no fence.proxy.async before p_full
+#define GRL_DIAG_PFENCE(stmt)
+#else
+#define GRL_DIAG_PFENCE(stmt) stmt
+#endif
+#ifdef GRL_ATTN_DIAG_NOGATHER  // the producer gathers K / V only for the first tiles (the MMAs re-read stale tiles)
+#define GRL_DIAG_GATHER(stmt)
+#else
+#define GRL_DIAG_GATHER(stmt) stmt
+#endif
+
 constexpr int kAttnThreads = kQT + 32;  // 4 softmax warps (one query row per thread) + 1 producer / MMA warp
 
 // Warp-specialised pipeline without block-wide barriers in the loop (tiles t = 0..nt-1 of KT keys):
@@ -179,7 +213,7 @@ __global__ void __launch_bounds__(kAttnThreads, (KT <= 32 ? 4 : KT <= 64 ? 3 : 2
         }
       }
       // K buffer t&1 is free (QK(t) completed before anyone could read S_t)
-      if (t + 2 < ntiles) load_k(t + 2);
+      if (t + 2 < ntiles) GRL_DIAG_GATHER(load_k(t + 2));
       cp_async_commit();
       // ---- PV(t): V_t landed (second most recent group; K_{t+2} may still be in flight); P_t written and O_{t-1}
       // consumed by every row
@@ -200,7 +234,7 @@ __global__ void __launch_bounds__(kAttnThreads, (KT <= 32 ? 4 : KT <= 64 ? 3 : 2
       // V buffer (t+1)&1 held V_{t-1}.  PV(t-1) is complete: every row waited for it before arriving on p_full(t).
       // (Waiting on bar_o here would be wrong as well as redundant: PV(t) may already have flipped the barrier
       // again, and a parity wait on the older phase would then sleep until a phase that needs this warp.)
-      if (t + 1 < ntiles) load_v(t + 1);
+      if (t + 1 < ntiles) GRL_DIAG_GATHER(load_v(t + 1));
       cp_async_commit();
     }
     mbar_wait(bar_o, (ntiles - 1) & 1);  // keep TMEM alive until the last MMA is done
@@ -252,7 +286,7 @@ __global__ void __launch_bounds__(kAttnThreads, (KT <= 32 ? 4 : KT <= 64 ? 3 : 2
             const float4* bp = reinterpret_cast<const float4*>(bias_h + (size_t)cpy * a.rows_pad + (s0 + cpy));
 #pragma unroll
             for (int qd = 0; qd < RW / 4; ++qd) {
-              const float4 bb = __ldg(bp - qd);
+              const float4 bb = GRL_DIAG_BIAS(bp - qd);
               const int j = c0 + r0 + 4 * qd;
               lg[j + 0] = __uint_as_float(v[r0 + 4 * qd + 0]) + bb.w;
               lg[j + 1] = __uint_as_float(v[r0 + 4 * qd + 1]) + bb.z;
@@ -295,7 +329,7 @@ __global__ void __launch_bounds__(kAttnThreads, (KT <= 32 ? 4 : KT <= 64 ? 3 : 2
         float p[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-          p[e] = ex2(lg[c * 8 + e] - m_new);
+          p[e] = GRL_DIAG_EX2(lg[c * 8 + e] - m_new);
           if (!ones) ps[e & 3] += p[e];
         }
         uint4 pk;
@@ -307,7 +341,7 @@ __global__ void __launch_bounds__(kAttnThreads, (KT <= 32 ? 4 : KT <= 64 ? 3 : 2
           *reinterpret_cast<uint4*>(Pt + sw64(tid, c)) = pk;
         } else {  // [128 x KT] K-major SWIZZLE_128B, 64-key sub-tiles of 16 KB
           const int sub = c >> 3, cc = c & 7;
-          *reinterpret_cast<uint4*>(Pt + sub * (kQT * 128) + tid * 128 + ((cc ^ (tid & 7)) << 4)) = pk;
+          GRL_DIAG_PSTORE(*reinterpret_cast<uint4*>(Pt + sub * (kQT * 128) + tid * 128 + ((cc ^ (tid & 7)) << 4)) = pk);
         }
       }
       l_run = l_run * corr + ((ps[0] + ps[1]) + (ps[2] + ps[3]));
@@ -317,15 +351,17 @@ __global__ void __launch_bounds__(kAttnThreads, (KT <= 32 ? 4 : KT <= 64 ? 3 : 2
       if (t > 0) {
         mbar_wait(bar_o, (t - 1) & 1);
         tcgen05_fence_after();
-        uint32_t v[32];
-        tmem_ld32(trow + KT, v);
-        tmem_ld_wait();
+        GRL_DIAG_FOLD({
+          uint32_t v[32];
+          tmem_ld32(trow + KT, v);
+          tmem_ld_wait();
 #pragma unroll
-        for (int e = 0; e < kDP; ++e) o[e] = fmaf(o[e], corr_prev, __uint_as_float(v[e]));
+          for (int e = 0; e < kDP; ++e) o[e] = fmaf(o[e], corr_prev, __uint_as_float(v[e]));
+        })
       }
       corr_prev = corr;
       tcgen05_fence_before();
-      fence_proxy_async_smem();  // P_t (generic-proxy stores) -> visible to the tensor core
+      GRL_DIAG_PFENCE(fence_proxy_async_smem());  // P_t (generic-proxy stores) -> visible to the tensor core
       mbar_arrive(p_full);
     }
     {
