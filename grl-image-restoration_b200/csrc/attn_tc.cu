@@ -26,9 +26,9 @@
 namespace grl {
 namespace tc {
 
-// ---- differential-timing builds (tools/attn_diag.py): each GRL_ATTN_DIAG_* define removes ONE ingredient of the kernel
+// ---- differential-timing builds (tools/kernel_diag.py): each GRL_ATTN_DIAG_* define removes ONE ingredient of the kernel
 // so that its cost shows up as a time difference.  The results of such a build are WRONG by construction; nothing but
-// tools/attn_diag.py defines these, and the default build is bit-for-bit the production kernel.
+// tools/kernel_diag.py defines these, and the default build is bit-for-bit the production kernel.
 #ifdef GRL_ATTN_DIAG_NOBIAS  // no bias-table loads (logits = S)
 #define GRL_DIAG_BIAS(ptr) make_float4(0.f, 0.f, 0.f, 0.f)
 #else

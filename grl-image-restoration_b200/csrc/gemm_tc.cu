@@ -62,6 +62,30 @@ __device__ __forceinline__ float tc_act(float v, int act, float slope) {
   return v;
 }
 
+// ---- differential-timing builds (tools/kernel_diag.py): each GRL_GEMM_DIAG_* define removes ONE stream of the
+// epilogue so that its cost shows up as a time difference.  Results of such builds are wrong by construction; the
+// default build is bit-for-bit the production kernel.
+#ifdef GRL_GEMM_DIAG_NORES  // fp32 residual tile never fetched
+#define GRL_GDIAG_RES(x) false
+#else
+#define GRL_GDIAG_RES(x) (x)
+#endif
+#ifdef GRL_GEMM_DIAG_NOCAB  // CAB features / gate never fetched
+#define GRL_GDIAG_CAB(x) false
+#else
+#define GRL_GDIAG_CAB(x) (x)
+#endif
+#ifdef GRL_GEMM_DIAG_NOST32  // fp32 residual stream never written
+#define GRL_GDIAG_ST32(x) false
+#else
+#define GRL_GDIAG_ST32(x) (x)
+#endif
+#ifdef GRL_GEMM_DIAG_NOST16  // 16-bit operand copy never written
+#define GRL_GDIAG_ST16(x) false
+#else
+#define GRL_GDIAG_ST16(x) (x)
+#endif
+
 constexpr int kStages = 2;
 constexpr int kBM = 128, kBK = 64;
 constexpr int kTH = 8, kTW = 16;  // conv patch (kTH * kTW == kBM)
@@ -254,7 +278,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // ---------------- residual tile -> staging, asynchronously (cp.async, 16 B per request, the whole 128 x C
       // tile in flight at once); it lands while the row moments are computed from TMEM.  Phase A then adds its
       // result in place, so phase B has no fp32 loads left.
-      const bool res_in_stage = a.res_f32 != nullptr;
+      const bool res_in_stage = GRL_GDIAG_RES(a.res_f32 != nullptr);
       if (res_in_stage) {
         const int C4r = Cw >> 2, ewr = et >> 5;
         for (int r = ewr; r < kBM; r += 4) {
@@ -336,7 +360,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int C4 = Cw >> 2;                              // float4 items with real data
       const int P4 = out16 ? (int)(a.ldo_bf16 >> 2) : C4;  // the 16-bit copy is written up to its (zero) pad
       const int ew = et >> 5;
-      const bool has_cab = (EPI == EPI_LN) && a.cab_y != nullptr;
+      const bool has_cab = GRL_GDIAG_CAB((EPI == EPI_LN) && a.cab_y != nullptr);
       const uint16_t* caby = reinterpret_cast<const uint16_t*>(a.cab_y);
       constexpr int RB = 8;
       for (int cbase = 0; cbase < P4; cbase += 32) {
@@ -369,9 +393,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 val.x = fmaf(c01.x, gg[i].x, val.x), val.y = fmaf(c01.y, gg[i].y, val.y);
                 val.z = fmaf(c23.x, gg[i].z, val.z), val.w = fmaf(c23.y, gg[i].w, val.w);
               }
-              if (a.out_f32) *reinterpret_cast<float4*>(a.out_f32 + tok[i] * a.ldo_f32 + c4 * 4) = val;
+              if (GRL_GDIAG_ST32(a.out_f32)) *reinterpret_cast<float4*>(a.out_f32 + tok[i] * a.ldo_f32 + c4 * 4) = val;
             }
-            if (out16)
+            if (GRL_GDIAG_ST16(out16))
               *reinterpret_cast<uint2*>(out16 + tok[i] * a.ldo_bf16 + c4 * 4) =
                   make_uint2(pack16(val.x, val.y, fmt), pack16(val.z, val.w, fmt));
           }
@@ -418,7 +442,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const long long tok = s_tok[r];
         if (tok < 0) continue;
         for (int vv = lane; vv < nvec; vv += 32)
-          *reinterpret_cast<uint4*>(out16 + tok * a.ldo_bf16 + n0 + vv * 8) = *reinterpret_cast<const uint4*>(stg + r * P16 + vv * 8);
+          if (GRL_GDIAG_ST16(true))
+            *reinterpret_cast<uint4*>(out16 + tok * a.ldo_bf16 + n0 + vv * 8) = *reinterpret_cast<const uint4*>(stg + r * P16 + vv * 8);
       }
     }
   }

@@ -1,13 +1,14 @@
-"""Dev tool: differential timing of the attention kernel (what does each ingredient cost?).
+"""Dev tool: differential timing of the attention and GEMM kernels (what does each ingredient cost?).
 
 Two steps, because nvcc is in the build container and the GPU is not:
 
-  python tools/attn_diag.py build      # here: one libgrl_b200.so per GRL_ATTN_DIAG_* define -> ab/lib<name>.so
-  gpurun -- python tools/attn_diag.py run [--batch 8]
+  python tools/kernel_diag.py build     # here: one libgrl_b200.so per GRL_*_DIAG_* define -> ab/lib<name>.so
+  gpurun -- python tools/kernel_diag.py run [--batch 8]
                                         # on the B200: times one GRL-Base x4 forward per variant with CUDA events
 
 `run` swaps each library into place, launches tools/time_model.py in a fresh process and restores the production
-library at the end.  Variants other than `base` compute garbage on purpose (attn_tc.cu, GRL_DIAG_* macros): only their
+library at the end.  Variants other than `base` compute garbage on purpose (attn_tc.cu GRL_DIAG_*, gemm_tc.cu
+GRL_GDIAG_* macros): only their
 TIME means anything.  ab/ is scratch (git-ignored) but travels to the GPU box -- delete it when done (16 MB / variant).
 Caveat: with the ones-column denominators nothing else consumes P, so `nopstore` also removes the exp2 (dead code).
 """
@@ -32,15 +33,22 @@ VARIANTS = {
     "nogather": "-DGRL_ATTN_DIAG_NOGATHER",
     "nobias_noexp": "-DGRL_ATTN_DIAG_NOBIAS -DGRL_ATTN_DIAG_NOEXP",
     "softmax_stub": "-DGRL_ATTN_DIAG_NOBIAS -DGRL_ATTN_DIAG_NOEXP -DGRL_ATTN_DIAG_NOPSTORE -DGRL_ATTN_DIAG_NOFOLD",
+    "gemm_nores": "-DGRL_GEMM_DIAG_NORES",
+    "gemm_nocab": "-DGRL_GEMM_DIAG_NOCAB",
+    "gemm_nost32": "-DGRL_GEMM_DIAG_NOST32",
+    "gemm_nost16": "-DGRL_GEMM_DIAG_NOST16",
+    "gemm_noepi_io": "-DGRL_GEMM_DIAG_NORES -DGRL_GEMM_DIAG_NOCAB -DGRL_GEMM_DIAG_NOST32 -DGRL_GEMM_DIAG_NOST16",
 }
 
 
-def build():
+def build(only=None):
     sys.path.insert(0, PKG)
     import build as b
 
     os.makedirs(AB, exist_ok=True)
     for name, defs in VARIANTS.items():
+        if only and name not in only and name != "base":
+            continue
         os.environ["GRL_NVCC_DEFINES"] = defs
         b.build(force=True)
         shutil.copy(LIB, os.path.join(AB, f"lib{name}.so"))
@@ -57,7 +65,7 @@ def run(batch, precision):
         for name in VARIANTS:
             src = os.path.join(AB, f"lib{name}.so")
             if not os.path.exists(src):
-                print("missing", src, "- run `attn_diag.py build` first")
+                print("missing", src, "- run `kernel_diag.py build` first")
                 continue
             shutil.copy(src, LIB)
             out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "time_model.py"), "--variant", "base", "--size",
@@ -80,5 +88,6 @@ if __name__ == "__main__":
     ap.add_argument("cmd", choices=["build", "run"])
     ap.add_argument("--batch", type=int, default=8)
     ap.add_argument("--precision", default="fp16")
+    ap.add_argument("--only", default="", help="comma list of variants to build (base is always built)")
     a = ap.parse_args()
-    build() if a.cmd == "build" else run(a.batch, a.precision)
+    build([v for v in a.only.split(",") if v]) if a.cmd == "build" else run(a.batch, a.precision)
