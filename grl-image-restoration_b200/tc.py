@@ -8,7 +8,6 @@ statistics and every accumulator are fp32.
 Reference semantics: mixed_attn_block_efficient.py:351-381,:539-556; mixed_attn_block.py:948-983; grl.py:164-170,:506-551.
 """
 import ctypes
-import math
 
 import torch
 
