@@ -60,3 +60,51 @@ def test_stripe_info(pkg, oracle):
 def test_bad_geometry_is_an_error(pkg):
     with pytest.raises(RuntimeError):
         pkg.geometry.shift_mask((30, 30), (8, 8), (4, 4))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# property tests: random geometries (beyond the released configurations) against the oracle's tensor constructions
+# ---------------------------------------------------------------------------------------------------------------
+from hypothesis import given, settings  # noqa: E402
+from hypothesis import strategies as st  # noqa: E402
+
+
+@st.composite
+def _geometry(draw):
+    df = draw(st.sampled_from([1, 2, 3, 4]))
+    wh, ww = draw(st.integers(1, 6)) * df, draw(st.integers(1, 6)) * df  # window sides: multiples of df
+    wh, ww = max(wh, 2 * df if df == 1 else df), max(ww, 2 * df if df == 1 else df)  # a side of 1 divides by zero in the reference too
+    nh, nw = draw(st.integers(1, 3)), draw(st.integers(1, 3))            # windows per axis
+    sh = draw(st.integers(0, wh // df)) * df if wh > df else 0          # shifts: multiples of df (anchors shift by s // df)
+    sw = draw(st.integers(0, ww // df)) * df if ww > df else 0
+    return (nh * wh, nw * ww), (wh, ww), (min(sh, wh - 1) // df * df, min(sw, ww - 1) // df * df), df
+
+
+@settings(max_examples=60, deadline=None)
+@given(_geometry())
+def test_random_geometries_bit_exact(pkg, oracle, geo):
+    res, ws, sh, df = geo
+    G = pkg.geometry
+    assert torch.equal(G.coords_table(ws, df), oracle.coords_table(list(ws), df))
+    for w2a in (True, False):
+        assert torch.equal(G.position_index(ws, df, w2a), oracle.position_index(list(ws), df, w2a))
+        assert torch.equal(G.shift_mask(res, ws, sh, df, w2a), oracle.shift_mask(list(res), list(ws), list(sh), df, w2a))
+
+
+@settings(max_examples=200, deadline=None)
+@given(st.integers(8, 2000), st.integers(8, 600), st.integers(0, 64))
+def test_tile_origins_match_engine_loop(pkg, size, tile, overlap):
+    """engines/base.py:95-99: stride = tile - overlap; range(0, size - tile, stride) + [size - tile]."""
+    from grl_image_restoration_b200 import tiling
+
+    tile = min(tile, size)
+    if overlap >= tile:
+        return
+    got = tiling.tile_origins(size, tile, overlap)
+    assert got[-1] == size - tile and got[0] == 0 or size == tile
+    assert all(0 <= o <= size - tile for o in got)
+    covered = set()
+    for o in got:
+        covered.update(range(o, o + tile))
+    assert covered == set(range(size)), "every pixel is restored by at least one tile"
+    assert got[:-1] == list(range(0, size - tile, tile - overlap))
