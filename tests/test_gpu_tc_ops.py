@@ -21,10 +21,10 @@ def bf(t, fmt=0):
     return t.to(torch.bfloat16 if fmt else torch.float16).float()
 
 
-# Attention kernel variants (grl_tc_attn_variant): 0 = production.  The experimental two-threads-per-row kernels (1, 2)
-# are exercised by the same tests only on request -- GRL_TEST_EXPERIMENTAL=1 -- because a faulting experimental kernel
+# Attention kernel variants (grl_tc_attn_variant): 0 = production.  The experimental kernels (1, 2: two threads per row;
+# 3: TMA producer) are exercised by the same tests only on request -- GRL_TEST_EXPERIMENTAL=1 -- because a faulting experimental kernel
 # would poison the CUDA context of the whole pytest process.
-ATTN_VARIANTS = [0, 1, 2] if os.environ.get("GRL_TEST_EXPERIMENTAL") == "1" else [0]
+ATTN_VARIANTS = [0, 1, 2, 3] if os.environ.get("GRL_TEST_EXPERIMENTAL") == "1" else [0]
 
 
 @pytest.fixture(scope="module", params=ATTN_VARIANTS, ids=lambda v: f"attn{v}")
