@@ -50,6 +50,8 @@ _SIGNATURES = {
     "grl_launch_count": (ctypes.c_uint64, []),
     "grl_rel_index_host": (c_int, [c_int, c_int, c_int, c_int, c_vp]),
     "grl_shift_mask_host": (c_int, [c_int] * 8 + [c_vp]),
+    "grl_token_map_host": (c_int, [GrlGrid, c_vp]),
+    "grl_tc_attn_box_tokens": (c_int, [GrlGrid]),
     "grl_coords_table_host": (c_int, [c_int, c_int, c_int, c_vp]),
     "grl_bias_table_f32": (c_int, [c_vp, c_int, c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_vp]),
     "grl_tc_bias_table4": (c_int, [c_vp, c_int, c_vp, c_vp, c_vp, c_int, c_int, c_f32, c_int, c_vp, c_vp]),

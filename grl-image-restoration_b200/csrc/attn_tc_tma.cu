@@ -362,7 +362,7 @@ __global__ void __launch_bounds__(kAttnThreads, (KT <= 32 ? 4 : KT <= 64 ? 3 : 2
 // ---------------------------------------------------------------------------------------------------------------
 // Tokens per box for a window of width ww rolled by sw: the largest power of two <= 64 dividing gcd(ww, sw) (ww if the
 // grid is not rolled horizontally).  0 = no usable box (odd widths, or runs shorter than 4 tokens = 256 bytes).
-int box_tokens(const GrlGrid& g) {
+int box_tokens_impl(const GrlGrid& g) {
   int d = g.ww;
   if (g.sw > 0) {
     int x = g.ww, y = g.sw;
@@ -432,12 +432,14 @@ int launch_tma_kw(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMa
 
 }  // namespace
 
+int attn_tma_box_tokens(const GrlGrid& g) { return box_tokens_impl(g); }
+
 // Returns GRL_OK after launching, a negative error, or +1 when this geometry cannot be expressed as TMA boxes (the
 // caller then launches the gather kernel).  Arguments already validated by launch_attn_tc.
 int launch_attn_tc_tma(const AttnTcArgs& a, unsigned nblk, cudaStream_t st) {
   AttnTmaGeom tg;
-  tg.bw_q = box_tokens(a.gq);
-  tg.bw_k = box_tokens(a.gk);
+  tg.bw_q = box_tokens_impl(a.gq);
+  tg.bw_k = box_tokens_impl(a.gk);
   if (tg.bw_q == 0 || tg.bw_k == 0) return 1;
   // 16-byte alignment of every box origin / pitch (checked by capi for pitches and offsets; bases come from torch)
   if ((reinterpret_cast<uintptr_t>(a.q) | reinterpret_cast<uintptr_t>(a.k) | reinterpret_cast<uintptr_t>(a.v)) & 15) return 1;

@@ -46,6 +46,25 @@ int grl_rel_index_host(int wh, int ww, int df, int window_to_anchor, int64_t* ou
   return GRL_OK;
 }
 
+int grl_token_map_host(GrlGrid g, int32_t* out) {
+  GRL_REQUIRE(out != nullptr, "token_map: null output");
+  int rc;
+  if ((rc = check_grid(g, "token_map")) != GRL_OK) return rc;
+  const int nwh = g.H / g.wh, nww = g.W / g.ww, n = g.wh * g.ww;
+  for (int wr = 0; wr < nwh; ++wr)
+    for (int wc = 0; wc < nww; ++wc)
+      for (int i = 0; i < n; ++i) {
+        const Tok t = locate(g, wr, wc, i);
+        out[((size_t)wr * nww + wc) * n + i] = t.y * g.W + t.x;
+      }
+  return GRL_OK;
+}
+
+int grl_tc_attn_box_tokens(GrlGrid g) {
+  if (check_grid(g, "attn_box_tokens") != GRL_OK) return 0;
+  return tc::attn_tma_box_tokens(g);
+}
+
 int grl_shift_mask_host(int H, int W, int wh, int ww, int sh, int sw, int df, int window_to_anchor, float* out) {
   GRL_REQUIRE(df > 0 && out, "shift_mask: bad arguments");
   GrlGrid gt = {H, W, wh, ww, sh, sw};

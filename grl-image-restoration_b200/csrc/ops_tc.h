@@ -83,6 +83,7 @@ int attn_variant(int set);  // -1 (or anything outside {0,1,2,3}): query only; r
 int launch_attn_tc_split(const AttnTcArgs& a, unsigned nblk, int mode, cudaStream_t st);
 // experimental TMA-producer variant (attn_tc_tma.cu), variant 3; returns +1 when the geometry has no TMA box form
 int launch_attn_tc_tma(const AttnTcArgs& a, unsigned nblk, cudaStream_t st);
+int attn_tma_box_tokens(const GrlGrid& g);
 
 }  // namespace tc
 }  // namespace grl

@@ -60,6 +60,13 @@ int grl_rel_index_host(int wh, int ww, int df, int window_to_anchor, int64_t* ou
 int grl_shift_mask_host(int H, int W, int wh, int ww, int sh, int sw, int df, int window_to_anchor, float* out);
 /* get_relative_coords_table_all (ops.py:225-271), pretrained size 0: out is ((wh+awh-1)*(ww+aww-1), 2) fp32 */
 int grl_coords_table_host(int wh, int ww, int df, float* out);
+/* torch.roll(-shift) + window_partition (ops.py:36-53, efficient.py:141-143,:236-241) as a gather map: out is
+ * (nW, wh*ww) int32, the flat index y*W + x (un-rolled image) of token n of window w -- the addressing every attention
+ * kernel folds into its loads and stores. */
+int grl_token_map_host(GrlGrid g, int32_t* out);
+/* Tokens per TMA box of the experimental TMA-producer attention kernel for this grid (attn_tc_tma.cu): runs of that many
+ * tokens starting at multiples of it are contiguous in memory for every window.  0 = no box form (gather kernel). */
+int grl_tc_attn_box_tokens(GrlGrid g);
 
 /* ---- fp32 operators (exact-parity path; every one is a hand-written sm_100a kernel) ---------- */
 
