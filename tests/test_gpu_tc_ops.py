@@ -24,15 +24,18 @@ def bf(t, fmt=0):
 # Attention kernel variants (grl_tc_attn_variant): 0 = production.  The experimental kernels (1, 2: two threads per row;
 # 3: TMA producer) are exercised by the same tests only on request -- GRL_TEST_EXPERIMENTAL=1 -- because a faulting experimental kernel
 # would poison the CUDA context of the whole pytest process.
-ATTN_VARIANTS = [0, 1, 2, 3] if os.environ.get("GRL_TEST_EXPERIMENTAL") == "1" else [0]
+ATTN_VARIANTS = [0, 1, 2, 3] if os.environ.get("GRL_TEST_EXPERIMENTAL") == "1" else [None]  # None: whatever GRL_ATTN_SPLIT says
 
 
-@pytest.fixture(scope="module", params=ATTN_VARIANTS, ids=lambda v: f"attn{v}")
+@pytest.fixture(scope="module", params=ATTN_VARIANTS, ids=lambda v: "attn" if v is None else f"attn{v}")
 def tc(pkg, device, request):
     from grl_image_restoration_b200 import capi, tc as T
 
     if capi.lib().grl_device_ok() != 1:
         pytest.skip("tcgen05 path needs sm_100")
+    if request.param is None:
+        yield T
+        return
     prev = capi.lib().grl_tc_attn_variant(request.param)
     yield T
     capi.lib().grl_tc_attn_variant(prev)
