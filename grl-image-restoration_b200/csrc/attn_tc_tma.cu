@@ -162,31 +162,32 @@ __global__ void __launch_bounds__(kAttnThreads, (KT <= 32 ? 4 : KT <= 64 ? 3 : 2
     load_k(0);
     if (ntiles > 1) load_k(1);
     load_v(0);
-    mbar_wait(q_full, 0);
-    mbar_wait(&k_full[0], 0);
-    __syncwarp();
+    // Only lane 0 polls the barriers (it is also the MMA issuer); the other lanes park at __syncwarp, which orders their
+    // later TMA issues after what lane 0 observed, instead of burning issue slots in 31 more spin loops.
     if (lane == 0) {
+      mbar_wait(q_full, 0);
+      mbar_wait(&k_full[0], 0);
       tcgen05_fence_after();
       issue_qk(0);
     }
+    __syncwarp();
     for (int t = 0; t < ntiles; ++t) {
       // ---- QK(t+1): K_{t+1} landed (buffer (t+1)&1, its ((t+1)>>1)-th use); S columns free once every row read S_t
       if (t + 1 < ntiles) {
-        mbar_wait(&k_full[(t + 1) & 1], ((t + 1) >> 1) & 1);
-        mbar_wait(s_free, t & 1);
-        __syncwarp();
         if (lane == 0) {
+          mbar_wait(&k_full[(t + 1) & 1], ((t + 1) >> 1) & 1);
+          mbar_wait(s_free, t & 1);
           tcgen05_fence_after();
           issue_qk(t + 1);
         }
+        __syncwarp();
       }
       // K buffer t&1 and the koff / rid slot of tile t-1 are free (QK(t) completed before anyone could read S_t)
       if (t + 2 < ntiles) load_k(t + 2);
       // ---- PV(t): V_t landed; P_t written and O_{t-1} consumed by every row
-      mbar_wait(&v_full[t & 1], (t >> 1) & 1);
-      mbar_wait(p_full, t & 1);
-      __syncwarp();
       if (lane == 0) {
+        mbar_wait(&v_full[t & 1], (t >> 1) & 1);
+        mbar_wait(p_full, t & 1);
         tcgen05_fence_after();
         const uint32_t v_sa = smem_u32(Vs + (t & 1) * S::KV_BYTES);
         const uint32_t pt_sa = p_sa + (t & 1) * S::P_BYTES;
@@ -198,10 +199,12 @@ __global__ void __launch_bounds__(kAttnThreads, (KT <= 32 ? 4 : KT <= 64 ? 3 : 2
         }
         umma_commit(bar_o);
       }
+      __syncwarp();
       // V buffer (t+1)&1 held V_{t-1}; PV(t-1) is complete: every row waited for it before arriving on p_full(t)
       if (t + 1 < ntiles) load_v(t + 1);
     }
-    mbar_wait(bar_o, (ntiles - 1) & 1);  // keep TMEM alive until the last MMA is done
+    if (lane == 0) mbar_wait(bar_o, (ntiles - 1) & 1);  // keep TMEM alive until the last MMA is done
+    __syncwarp();
   } else {
     // =============================================================== softmax warps: thread = query row
     const int qi = qt * kQT + tid;
