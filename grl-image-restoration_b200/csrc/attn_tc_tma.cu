@@ -364,7 +364,7 @@ __global__ void __launch_bounds__(kAttnThreads, (KT <= 32 ? 4 : KT <= 64 ? 3 : 2
 // host side
 // ---------------------------------------------------------------------------------------------------------------
 // Tokens per box for a window of width ww rolled by sw: the largest power of two <= 64 dividing gcd(ww, sw) (ww if the
-// grid is not rolled horizontally).  0 = no usable box (odd widths, or runs shorter than 4 tokens = 256 bytes).
+// grid is not rolled horizontally).  0 = no usable box (odd widths, or runs shorter than 8 tokens = 512 bytes).
 int box_tokens_impl(const GrlGrid& g) {
   int d = g.ww;
   if (g.sw > 0) {
@@ -377,7 +377,7 @@ int box_tokens_impl(const GrlGrid& g) {
   }
   int bw = 64;
   while (bw > 1 && d % bw) bw >>= 1;
-  return bw >= 4 ? bw : 0;
+  return bw >= 8 ? bw : 0;  // >= 512 bytes per box: destinations stay aligned to the 64-byte-swizzle repeat
 }
 
 int make_token_map(CUtensorMap* m, const void* base, long long ld, const GrlGrid& g, int B, int bw) {

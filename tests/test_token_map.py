@@ -48,7 +48,7 @@ def test_tma_boxes_are_contiguous_runs(pkg, grid):
     box = capi.lib().grl_tc_attn_box_tokens(g)
     if box == 0:
         return
-    assert box >= 4 and box & (box - 1) == 0 and box <= 64 and ww % box == 0 and 64 % box == 0
+    assert box >= 8 and box & (box - 1) == 0 and box <= 64 and ww % box == 0 and 64 % box == 0
     runs = tm.view(tm.shape[0], -1, box)  # (window, run, token in run)
     first = runs[..., :1]
     assert torch.equal(runs, first + torch.arange(box, dtype=torch.int32)), "a box must be consecutive pixels"
@@ -57,7 +57,7 @@ def test_tma_boxes_are_contiguous_runs(pkg, grid):
 
 @pytest.mark.parametrize("grid,box", [((256, 256, 32, 32, 16, 16), 16), ((256, 256, 32, 32, 0, 0), 32), ((256, 256, 64, 64, 32, 32), 32),
                                       ((128, 128, 32, 32, 16, 16), 16), ((256, 256, 64, 128, 0, 0), 64), ((96, 96, 12, 12, 6, 6), 0),
-                                      ((96, 192, 48, 96, 24, 48), 16), ((56, 40, 7, 5, 3, 2), 0), ((64, 64, 8, 8, 4, 4), 4)])
+                                      ((96, 192, 48, 96, 24, 48), 16), ((56, 40, 7, 5, 3, 2), 0), ((64, 64, 8, 8, 4, 4), 0), ((64, 64, 16, 16, 8, 8), 8)])
 def test_box_tokens_of_released_geometries(pkg, grid, box):
     from grl_image_restoration_b200 import capi
 
