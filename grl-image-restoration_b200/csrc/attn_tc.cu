@@ -420,10 +420,10 @@ int attn_variant(int set) {
   if (variant < 0) {
     const char* e = getenv("GRL_ATTN_SPLIT");
     const int v = e ? atoi(e) : 0;
-    variant = (v >= 1 && v <= 3) ? v : 0;
+    variant = (v >= 1 && v <= 4) ? v : 0;
   }
   const int prev = variant;
-  if (set >= 0 && set <= 3) variant = set;
+  if (set >= 0 && set <= 4) variant = set;
   return prev;
 }
 
@@ -442,8 +442,8 @@ int launch_attn_tc(const AttnTcArgs& a, cudaStream_t st) {
   GRL_REQUIRE(nblk < (1ll << 31), "attn_tc: grid too large");
   const int split = attn_variant(-1);  // 1 | 2: experimental two-threads-per-row kernel (attn_tc_split.cu), default 0
   if (split == 1 || split == 2) return launch_attn_tc_split(a, (unsigned)nblk, split, st);
-  if (split == 3) {  // TMA producer where the geometry allows it, else fall through to the gather kernel
-    const int rc = launch_attn_tc_tma(a, (unsigned)nblk, st);
+  if (split == 3 || split == 4) {  // TMA producer where the geometry allows it, else fall through to the gather kernel
+    const int rc = launch_attn_tc_tma(a, (unsigned)nblk, split == 4, st);
     if (rc <= 0) return rc;
   }
   // 64 keys per tile, 3 CTAs / SM (32- and 128-key tiles were measured slower: profiles/r1_tc_path_final.md)

@@ -25,17 +25,27 @@ namespace {
 
 constexpr int kAttnThreads = kQT + 32;
 
+// Optional staging area for the bias rows of a key tile (template SB): two buffers after the barriers
+template <int KT, bool SB>
+struct AttnTmaSmem : AttnSmem<KT> {
+  static constexpr int BIAS_BYTES = 7168;  // per buffer: up to (rows of a tile) x 4 shifted copies x padded row
+  static constexpr int OFF_BIAS = AttnSmem<KT>::OFF_BAR + 128;
+  static constexpr int TOTAL = SB ? OFF_BIAS + 2 * BIAS_BYTES + 1024 : AttnSmem<KT>::TOTAL;
+};
+
 struct AttnTmaGeom {
   int bw_q, bw_k;  // tokens per TMA box (power of two, divides gcd(window width, horizontal shift) and the tile sizes)
 };
 
-template <int KT, int KW, int VAR>
+// SB: the producer stages the few bias-table rows a (query tile, key tile) pair needs in shared memory with 1-D bulk
+// copies, and the softmax threads read their aligned float4 runs from there instead of from global memory / L1.
+template <int KT, int KW, int VAR, bool SB>
 __global__ void __launch_bounds__(kAttnThreads, (KT <= 32 ? 4 : KT <= 64 ? 3 : 2)) attn_tc_tma_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                    const __grid_constant__ CUtensorMap tmV, const AttnTcArgs a, const AttnTmaGeom tg) {
   static_assert(KT == 32 || KT == 64 || KT == 128, "P tiles: 64-byte rows (SWIZZLE_64B) or 128-byte rows (SWIZZLE_128B)");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  using S = AttnSmem<KT>;
+  using S = AttnTmaSmem<KT, SB>;
   uint8_t* Qs = smem;
   uint8_t* Ks = smem + S::OFF_K;
   uint8_t* Vs = smem + S::OFF_V;
@@ -50,7 +60,9 @@ __global__ void __launch_bounds__(kAttnThreads, (KT <= 32 ? 4 : KT <= 64 ? 3 : 2
   uint64_t* q_full = bar_s + 7;                                       // Q tile landed            (TMA complete_tx)
   uint64_t* k_full = bar_s + 8;                                       // [2] K_t landed
   uint64_t* v_full = bar_s + 10;                                      // [2] V_t landed
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_s + 12);
+  uint64_t* bias_full = bar_s + 12;                                   // [2] staged bias rows of tile t landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_s + 14);
+  float* bias_s = reinterpret_cast<float*>(smem + S::OFF_BIAS);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int Nq = a.gq.wh * a.gq.ww, Nk = a.gk.wh * a.gk.ww;
@@ -76,7 +88,7 @@ __global__ void __launch_bounds__(kAttnThreads, (KT <= 32 ? 4 : KT <= 64 ? 3 : 2
     mbar_init(p_full, kQT);
     for (int i = 0; i < 3; ++i) mbar_init(&meta_full[i], 32);
     mbar_init(q_full, 1);
-    for (int i = 0; i < 2; ++i) mbar_init(&k_full[i], 1), mbar_init(&v_full[i], 1);
+    for (int i = 0; i < 2; ++i) mbar_init(&k_full[i], 1), mbar_init(&v_full[i], 1), mbar_init(&bias_full[i], 1);
     mbar_init_fence();
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmK);
@@ -88,6 +100,17 @@ __global__ void __launch_bounds__(kAttnThreads, (KT <= 32 ? 4 : KT <= 64 ? 3 : 2
   tcgen05_fence_after();
   const uint32_t tmem = *tmem_slot;
   const bool need_mask_cta = a.use_mask && (wr == nwh - 1 || wc == nww - 1);
+  // ---- staged bias (SB): a (query row ih, key row kh) pair only needs table row ih - kh + KH - 1; a 128-query tile
+  // spans few query rows and a 64-key tile few key rows, so a handful of rows of Wt floats covers the whole 128 x 64
+  // bias tile.  Four copies, copy c shifted right by c entries, so every thread's reversed runs of 4 consecutive entries
+  // are aligned 16-byte shared-memory loads (same trick as the global table).
+  constexpr int KWc = KW > 0 ? KW : 4;
+  const int RP = ((Wt + 8) + 3) & ~3;                                  // padded row length (floats)
+  const int ih_a = (qt * kQT) / a.gq.ww;                                // query rows of this tile
+  const int ih_b = min(Nq - 1, qt * kQT + kQT - 1) / a.gq.ww;
+  const int krows_max = (KWc >= KT) ? 1 : KT / KWc;
+  const bool use_sb = SB && (KW > 0) && ((ih_b - ih_a) + krows_max) * 4 * RP * 4 <= S::BIAS_BYTES && a.rows_pad >= a.rows + 16;
+  const float* bias_hd = a.bias + (size_t)h * 4 * a.rows_pad;          // copy c of this head: bias_hd + c * rows_pad
   constexpr int fmt = (VAR & 1) ? FMT_BF16 : FMT_F16;
 
   if (warp == 4) {
@@ -110,6 +133,22 @@ __global__ void __launch_bounds__(kAttnThreads, (KT <= 32 ? 4 : KT <= 64 ? 3 : 2
         tma_load_4d(dst + s * bw * 64, map, bar, coff, x, y, b);
       }
     };
+    auto load_bias = [&](int tile) {  // rows needed by (this query tile) x (key tile `tile`); full tiles only
+      const int k0 = tile * KT;
+      if (!use_sb || k0 + KT > Nk) return;
+      const int kh_a = k0 / KWc, kh_b = (k0 + KT - 1) / KWc;
+      const int dmin = ih_a - kh_b;
+      const int nrow = ((ih_b - ih_a) + (kh_b - kh_a) + 1) * 4;  // one bulk copy per (row, copy): RP floats each
+      float* R = bias_s + (tile & 1) * (S::BIAS_BYTES / 4);
+      uint64_t* bar = &bias_full[tile & 1];
+      if (lane == 0) mbar_expect_tx(bar, (uint32_t)(nrow * RP * 4));
+      __syncwarp();
+      for (int i = lane; i < nrow; i += 32) {
+        const int u = (dmin + (i >> 2) + a.gk.wh - 1) * Wt - (i & 3);  // table index that lands at R_c[0]
+        const int g0 = (u + 3) & ~3;                                  // aligned start inside global copy g0 - u
+        bulk_load_1d(R + i * RP, bias_hd + (size_t)(g0 - u) * a.rows_pad + g0, (uint32_t)(RP * 4), bar);
+      }
+    };
     auto load_q = [&]() { tma_rows(&tmQ, a.gq, a.q_off + h * kDP, Qs, qt * kQT, min(kQT, Nq - qt * kQT), tg.bw_q, q_full); };
     // koff / rid of a key tile: only tiles that take the generic bias path (ragged last tile, KW == 0) or the shift
     // mask read them
@@ -129,6 +168,7 @@ __global__ void __launch_bounds__(kAttnThreads, (KT <= 32 ? 4 : KT <= 64 ? 3 : 2
       const int k0 = tile * KT;
       tma_rows(&tmK, a.gk, a.k_off + h * kDP, Ks + (tile & 1) * S::KV_BYTES, k0, min(KT, Nk - k0), tg.bw_k, &k_full[tile & 1]);
       load_meta(tile);
+      load_bias(tile);  // same buffer discipline as K: every row is done with tile - 2's rows before s_free(tile - 2)
     };
     auto load_v = [&](int tile) {
       const int k0 = tile * KT, cnt = min(KT, Nk - k0);
@@ -209,7 +249,7 @@ __global__ void __launch_bounds__(kAttnThreads, (KT <= 32 ? 4 : KT <= 64 ? 3 : 2
     // =============================================================== softmax warps: thread = query row
     const int qi = qt * kQT + tid;
     const bool q_ok = qi < Nq;
-    const Tok tq = locate(a.gq, wr, wc, q_ok ? qi : 0);
+    const Tok tq = locate(a.gq, wr, wc, q_ok ? qi : qt * kQT);  // padding rows mirror the tile's first row
     const long long q_tok = (long long)(b * a.gq.H + tq.y) * a.gq.W + tq.x;
     const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
     // bias:  idx(i, j) = base_i - koff_j  (grl_geometry.h rel_index); table copy c holds T shifted right by c entries
@@ -234,6 +274,15 @@ __global__ void __launch_bounds__(kAttnThreads, (KT <= 32 ? 4 : KT <= 64 ? 3 : 2
       tcgen05_fence_after();
       const bool full_tile = (KW > 0) && (k0 + KT <= Nk);
       if (!full_tile || need_mask) mbar_wait(&meta_full[slot], (t / 3) & 1);
+      const bool sb_tile = full_tile && use_sb;
+      const float* Rrow = nullptr;  // this thread's copy of row slot 0, positioned so that [.. - 4 qd] are its runs
+      int dmin = 0;
+      if (sb_tile) {
+        mbar_wait(&bias_full[buf], (t >> 1) & 1);
+        dmin = ih_a - (k0 + KT - 1) / KWc;
+        const int cthr = (-tq.iw) & 3;  // (iw + KW - 1 - 3 + cthr) % 4 == 0 because KW % 4 == 0
+        Rrow = bias_s + buf * (S::BIAS_BYTES / 4) + cthr * RP + (tq.iw + KWc - 1 - 3 + cthr);
+      }
 
       // ---- logits of this tile (log2 domain): S from TMEM + bias
       float lg[KT];
@@ -248,12 +297,17 @@ __global__ void __launch_bounds__(kAttnThreads, (KT <= 32 ? 4 : KT <= 64 ? 3 : 2
 #pragma unroll
           for (int r0 = 0; r0 < 32; r0 += RW) {
             const int kj = k0 + c0 + r0;  // first key of the run (CTA-uniform, multiple of 4)
-            const int s0 = base_i - ((kj / KWS) * Wt + (kj % KWS)) - 3;  // table index of key kj + 3
-            const int cpy = (-s0) & 3;
-            const float4* bp = reinterpret_cast<const float4*>(bias_h + (size_t)cpy * a.rows_pad + (s0 + cpy));
+            const float4* bp;
+            if (sb_tile) {  // staged rows: row slot (ih - kh) - dmin, column iw - kw + KW - 1 (shifted by the copy)
+              bp = reinterpret_cast<const float4*>(Rrow + ((tq.ih - kj / KWS) - dmin) * 4 * RP - (kj % KWS));
+            } else {        // straight from the 4-copy table in global memory
+              const int s0 = base_i - ((kj / KWS) * Wt + (kj % KWS)) - 3;  // table index of key kj + 3
+              const int cpy = (-s0) & 3;
+              bp = reinterpret_cast<const float4*>(bias_h + (size_t)cpy * a.rows_pad + (s0 + cpy));
+            }
 #pragma unroll
             for (int qd = 0; qd < RW / 4; ++qd) {
-              const float4 bb = __ldg(bp - qd);
+              const float4 bb = sb_tile ? bp[-qd] : __ldg(bp - qd);
               const int j = c0 + r0 + 4 * qd;
               lg[j + 0] = __uint_as_float(v[r0 + 4 * qd + 0]) + bb.w;
               lg[j + 1] = __uint_as_float(v[r0 + 4 * qd + 1]) + bb.z;
@@ -408,28 +462,41 @@ int make_dense_map(CUtensorMap* m, const void* base, long long rows, int box_row
   return GRL_OK;
 }
 
-template <int KT, int KW, int VAR>
+template <int KT, int KW, int VAR, bool SB>
 int launch_tma_var(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnTcArgs& a,
                    const AttnTmaGeom& tg, unsigned nblk, cudaStream_t st) {
-  auto kern = attn_tc_tma_kernel<KT, KW, VAR>;
+  auto kern = attn_tc_tma_kernel<KT, KW, VAR, SB>;
   static bool configured = false;
   if (!configured) {
-    GRL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnSmem<KT>::TOTAL));
+    GRL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnTmaSmem<KT, SB>::TOTAL));
     configured = true;
   }
-  kern<<<nblk, kAttnThreads, AttnSmem<KT>::TOTAL, st>>>(tq, tk, tv, a, tg);
+  kern<<<nblk, kAttnThreads, AttnTmaSmem<KT, SB>::TOTAL, st>>>(tq, tk, tv, a, tg);
   GRL_LAUNCH_CHECK("attn_tc_tma_kernel");
   return GRL_OK;
 }
 
-template <int KW>
+template <int KW, bool SB>
 int launch_tma_kw(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnTcArgs& a,
                   const AttnTmaGeom& tg, unsigned nblk, cudaStream_t st) {
   switch ((a.fmt == FMT_BF16 ? 1 : 0) | (a.ones_col ? 2 : 0)) {
-    case 0: return launch_tma_var<64, KW, 0>(tq, tk, tv, a, tg, nblk, st);
-    case 1: return launch_tma_var<64, KW, 1>(tq, tk, tv, a, tg, nblk, st);
-    case 2: return launch_tma_var<64, KW, 2>(tq, tk, tv, a, tg, nblk, st);
-    default: return launch_tma_var<64, KW, 3>(tq, tk, tv, a, tg, nblk, st);
+    case 0: return launch_tma_var<64, KW, 0, SB>(tq, tk, tv, a, tg, nblk, st);
+    case 1: return launch_tma_var<64, KW, 1, SB>(tq, tk, tv, a, tg, nblk, st);
+    case 2: return launch_tma_var<64, KW, 2, SB>(tq, tk, tv, a, tg, nblk, st);
+    default: return launch_tma_var<64, KW, 3, SB>(tq, tk, tv, a, tg, nblk, st);
+  }
+}
+
+template <bool SB>
+int launch_tma_sb(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnTcArgs& a,
+                  const AttnTmaGeom& tg, unsigned nblk, cudaStream_t st) {
+  switch (a.gk.ww) {
+    case 8: return launch_tma_kw<8, SB>(tq, tk, tv, a, tg, nblk, st);
+    case 16: return launch_tma_kw<16, SB>(tq, tk, tv, a, tg, nblk, st);
+    case 32: return launch_tma_kw<32, SB>(tq, tk, tv, a, tg, nblk, st);
+    case 64: return launch_tma_kw<64, SB>(tq, tk, tv, a, tg, nblk, st);
+    case 128: return launch_tma_kw<128, SB>(tq, tk, tv, a, tg, nblk, st);
+    default: return launch_tma_kw<0, SB>(tq, tk, tv, a, tg, nblk, st);
   }
 }
 
@@ -439,7 +506,7 @@ int attn_tma_box_tokens(const GrlGrid& g) { return box_tokens_impl(g); }
 
 // Returns GRL_OK after launching, a negative error, or +1 when this geometry cannot be expressed as TMA boxes (the
 // caller then launches the gather kernel).  Arguments already validated by launch_attn_tc.
-int launch_attn_tc_tma(const AttnTcArgs& a, unsigned nblk, cudaStream_t st) {
+int launch_attn_tc_tma(const AttnTcArgs& a, unsigned nblk, bool staged_bias, cudaStream_t st) {
   AttnTmaGeom tg;
   tg.bw_q = box_tokens_impl(a.gq);
   tg.bw_k = box_tokens_impl(a.gk);
@@ -456,14 +523,7 @@ int launch_attn_tc_tma(const AttnTcArgs& a, unsigned nblk, cudaStream_t st) {
   } else {
     if ((rc = make_token_map(&tv, a.v, a.ldv, a.gk, a.B, tg.bw_k)) != GRL_OK) return rc;
   }
-  switch (a.gk.ww) {
-    case 8: return launch_tma_kw<8>(tq, tk, tv, a, tg, nblk, st);
-    case 16: return launch_tma_kw<16>(tq, tk, tv, a, tg, nblk, st);
-    case 32: return launch_tma_kw<32>(tq, tk, tv, a, tg, nblk, st);
-    case 64: return launch_tma_kw<64>(tq, tk, tv, a, tg, nblk, st);
-    case 128: return launch_tma_kw<128>(tq, tk, tv, a, tg, nblk, st);
-    default: return launch_tma_kw<0>(tq, tk, tv, a, tg, nblk, st);
-  }
+  return staged_bias ? launch_tma_sb<true>(tq, tk, tv, a, tg, nblk, st) : launch_tma_sb<false>(tq, tk, tv, a, tg, nblk, st);
 }
 
 }  // namespace tc

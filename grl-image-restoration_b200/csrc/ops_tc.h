@@ -79,10 +79,11 @@ struct AttnTcArgs {
 };
 int launch_attn_tc(const AttnTcArgs& a, cudaStream_t st);
 // experimental two-threads-per-row variant (attn_tc_split.cu); reached through launch_attn_tc when the variant is 1|2
-int attn_variant(int set);  // -1 (or anything outside {0,1,2,3}): query only; returns the previous value
+int attn_variant(int set);  // -1 (or anything outside {0..4}): query only; returns the previous value
 int launch_attn_tc_split(const AttnTcArgs& a, unsigned nblk, int mode, cudaStream_t st);
-// experimental TMA-producer variant (attn_tc_tma.cu), variant 3; returns +1 when the geometry has no TMA box form
-int launch_attn_tc_tma(const AttnTcArgs& a, unsigned nblk, cudaStream_t st);
+// experimental TMA-producer variants (attn_tc_tma.cu): 3, and 4 = 3 + bias rows staged in shared memory; returns +1 when
+// the geometry has no TMA box form
+int launch_attn_tc_tma(const AttnTcArgs& a, unsigned nblk, bool staged_bias, cudaStream_t st);
 int attn_tma_box_tokens(const GrlGrid& g);
 
 }  // namespace tc

@@ -138,7 +138,7 @@ def attention(gq, gk, q, q_off, k, k_off, v, v_off, out, o_off, B, heads, bias, 
 
 
 def bias_rows_pad(rows):
-    return round_up(rows + 4, 4)
+    return round_up(rows + 16, 4)  # slack for the aligned over-reads of the shifted copies (16: staged rows, variant 4)
 
 
 def shifted_copies(table_hr):

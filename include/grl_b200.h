@@ -227,9 +227,10 @@ typedef struct {
 int grl_tc_attn(const GrlTcAttn* p, void* stream);
 
 /* Kernel variant behind grl_tc_attn: 0 = one thread per query row, cp.async gathers (default); EXPERIMENTAL: 1 / 2 = two
- * threads per row at 2 / 3 CTAs per SM (attn_tc_split.cu), 3 = Q / K / V tiles fetched with TMA tensor copies
- * (attn_tc_tma.cu; geometries without a box form run variant 0).  Initial value: environment variable GRL_ATTN_SPLIT
- * (unset = 0).  Returns the previous value; a value outside {0..3} only queries.  Same results contract as variant 0. */
+ * threads per row at 2 / 3 CTAs per SM (attn_tc_split.cu), 3 = Q / K / V tiles fetched with TMA tensor copies, 4 = 3 +
+ * the bias rows of every key tile staged in shared memory by bulk copies (attn_tc_tma.cu; geometries without a box form
+ * run variant 0).  Initial value: environment variable GRL_ATTN_SPLIT
+ * (unset = 0).  Returns the previous value; a value outside {0..4} only queries.  Same results contract as variant 0. */
 int grl_tc_attn_variant(int variant);
 
 #ifdef __cplusplus

@@ -24,7 +24,7 @@ def bf(t, fmt=0):
 # Attention kernel variants (grl_tc_attn_variant): 0 = production.  The experimental kernels (1, 2: two threads per row;
 # 3: TMA producer) are exercised by the same tests only on request -- GRL_TEST_EXPERIMENTAL=1 -- because a faulting experimental kernel
 # would poison the CUDA context of the whole pytest process.
-ATTN_VARIANTS = [0, 1, 2, 3] if os.environ.get("GRL_TEST_EXPERIMENTAL") == "1" else [None]  # None: whatever GRL_ATTN_SPLIT says
+ATTN_VARIANTS = [0, 1, 2, 3, 4] if os.environ.get("GRL_TEST_EXPERIMENTAL") == "1" else [None]  # None: whatever GRL_ATTN_SPLIT says
 
 
 @pytest.fixture(scope="module", params=ATTN_VARIANTS, ids=lambda v: "attn" if v is None else f"attn{v}")
