@@ -60,6 +60,29 @@ namespace tc {
 #define GRL_DIAG_GATHER(stmt) stmt
 #endif
 
+// One 64-byte row of a Q / K / V tile -> shared memory.  Default: the lane that owns the row issues its four 16-byte
+// cp.async (a warp instruction then touches 32 different rows: 32 L1 tag requests, 32 shared-memory wavefronts).
+// GRL_ATTN_QUAD_GATHER (A/B build, tools/kernel_diag.py): the row address is handed to a quad of lanes by shuffle and
+// each warp instruction copies 8 whole rows (8 tag requests).  Same bytes, same layout, same results.
+#ifdef GRL_ATTN_QUAD_GATHER
+#define GRL_ROW_COPY(base, r, src, ok)                                                                      \
+  do {                                                                                                      \
+    const int r_first_ = (r) - lane;                                                                        \
+    _Pragma("unroll") for (int sub_ = 0; sub_ < 4; ++sub_) {                                                \
+      const int sl_ = sub_ * 8 + (lane >> 2);                                                               \
+      const unsigned long long p_ = __shfl_sync(0xffffffffu, (unsigned long long)(uintptr_t)(src), sl_);    \
+      const int ok_ = __shfl_sync(0xffffffffu, (int)(ok), sl_);                                             \
+      cp_async_16((base) + sw64(r_first_ + sl_, lane & 3),                                                  \
+                  reinterpret_cast<const __nv_bfloat16*>((uintptr_t)p_) + (lane & 3) * 8, ok_ != 0);        \
+    }                                                                                                       \
+  } while (0)
+#else
+#define GRL_ROW_COPY(base, r, src, ok)                                                      \
+  do {                                                                                      \
+    _Pragma("unroll") for (int c_ = 0; c_ < 4; ++c_) cp_async_16((base) + sw64((r), c_), (src) + c_ * 8, (ok)); \
+  } while (0)
+#endif
+
 constexpr int kAttnThreads = kQT + 32;  // 4 softmax warps (one query row per thread) + 1 producer / MMA warp
 
 // Warp-specialised pipeline without block-wide barriers in the loop (tiles t = 0..nt-1 of KT keys):
@@ -132,8 +155,7 @@ __global__ void __launch_bounds__(kAttnThreads, (KT <= 32 ? 4 : KT <= 64 ? 3 : 2
         const bool ok = qi < Nq;
         const Tok tq = locate(a.gq, wr, wc, ok ? qi : 0);
         const __nv_bfloat16* src = a.q + ((long long)(b * a.gq.H + tq.y) * a.gq.W + tq.x) * a.ldq + a.q_off + h * kDP;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) cp_async_16(Qs + sw64(r, c), src + c * 8, ok);
+        GRL_ROW_COPY(Qs, r, src, ok);
       }
     };
     auto load_k = [&](int tile) {
@@ -144,8 +166,7 @@ __global__ void __launch_bounds__(kAttnThreads, (KT <= 32 ? 4 : KT <= 64 ? 3 : 2
         const Tok tk = locate(a.gk, wr, wc, ok ? kj : 0);
         const __nv_bfloat16* ksrc = a.k + ((long long)(b * a.gk.H + tk.y) * a.gk.W + tk.x) * a.ldk + a.k_off + h * kDP;
         uint8_t* kd = Ks + buf * S::KV_BYTES;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) cp_async_16(kd + sw64(r, c), ksrc + c * 8, ok);
+        GRL_ROW_COPY(kd, r, ksrc, ok);
         koff_s[slot * KT + r] = tk.ih * Wt + tk.iw;
         krid_s[slot * KT + r] = region_id(a.gk, tk.r, tk.c);
       }
@@ -164,8 +185,7 @@ __global__ void __launch_bounds__(kAttnThreads, (KT <= 32 ? 4 : KT <= 64 ? 3 : 2
           vsrc = a.v + ((long long)(b * a.gk.H + tk.y) * a.gk.W + tk.x) * a.ldv + a.v_off + h * kDP;
         }
         uint8_t* vd = Vs + buf * S::KV_BYTES;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) cp_async_16(vd + sw64(r, c), vsrc + c * 8, ok);
+        GRL_ROW_COPY(vd, r, vsrc, ok);
       }
     };
     const uint32_t idesc_qk = umma_idesc(kQT, KT, fmt, 0, 0);

@@ -33,6 +33,7 @@ VARIANTS = {
     "nogather": "-DGRL_ATTN_DIAG_NOGATHER",
     "nobias_noexp": "-DGRL_ATTN_DIAG_NOBIAS -DGRL_ATTN_DIAG_NOEXP",
     "softmax_stub": "-DGRL_ATTN_DIAG_NOBIAS -DGRL_ATTN_DIAG_NOEXP -DGRL_ATTN_DIAG_NOPSTORE -DGRL_ATTN_DIAG_NOFOLD",
+    "quadgather": "-DGRL_ATTN_QUAD_GATHER",  # NOT a stub: same results, each LDGSTS warp instruction copies 8 whole rows
     "gemm_nores": "-DGRL_GEMM_DIAG_NORES",
     "gemm_nocab": "-DGRL_GEMM_DIAG_NOCAB",
     "gemm_nost32": "-DGRL_GEMM_DIAG_NOST32",
