@@ -375,8 +375,7 @@ __global__ void __launch_bounds__(kAttnThreads, (KT <= 32 ? 4 : KT <= 64 ? 3 : 2
           uint32_t v[32];
           tmem_ld32(trow + KT, v);
           tmem_ld_wait();
-#pragma unroll
-          for (int e = 0; e < kDP; ++e) o[e] = fmaf(o[e], corr_prev, __uint_as_float(v[e]));
+          _Pragma("unroll") for (int e = 0; e < kDP; ++e) o[e] = fmaf(o[e], corr_prev, __uint_as_float(v[e]));
         })
       }
       corr_prev = corr;
