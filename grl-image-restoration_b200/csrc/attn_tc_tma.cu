@@ -511,6 +511,7 @@ int launch_attn_tc_tma(const AttnTcArgs& a, unsigned nblk, bool staged_bias, cud
   tg.bw_q = box_tokens_impl(a.gq);
   tg.bw_k = box_tokens_impl(a.gk);
   if (tg.bw_q == 0 || tg.bw_k == 0) return 1;
+  if (a.gq.W < tg.bw_q || a.gk.W < tg.bw_k) return 1;
   // 16-byte alignment of every box origin / pitch (checked by capi for pitches and offsets; bases come from torch)
   if ((reinterpret_cast<uintptr_t>(a.q) | reinterpret_cast<uintptr_t>(a.k) | reinterpret_cast<uintptr_t>(a.v)) & 15) return 1;
   CUtensorMap tq, tk, tv;
@@ -519,6 +520,7 @@ int launch_attn_tc_tma(const AttnTcArgs& a, unsigned nblk, bool staged_bias, cud
   if ((rc = make_token_map(&tk, a.k, a.ldk, a.gk, a.B, tg.bw_k)) != GRL_OK) return rc;
   if (a.v_dense) {
     const long long rows = (long long)a.B * (a.gk.H / a.gk.wh) * (a.gk.W / a.gk.ww) * a.heads * a.gk.wh * a.gk.ww;
+    if (rows < 64) return 1;  // the dense-V box is 64 rows: keep it inside the tensor
     if ((rc = make_dense_map(&tv, a.v, rows, 64)) != GRL_OK) return rc;
   } else {
     if ((rc = make_token_map(&tv, a.v, a.ldv, a.gk, a.B, tg.bw_k)) != GRL_OK) return rc;
