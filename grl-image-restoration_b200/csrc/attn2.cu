@@ -1,0 +1,572 @@
+// attn2.cu -- persistent, warp-specialised fused cosine attention for sm_100a (WindowAttention and both passes of
+// AnchorStripeAttention; mixed_attn_block_efficient.py:77-94,:128-165,:215-270).  Same math and operands as attn_tc.cu
+// (packed 16-bit head slots, q^ / k^ pre-normalised and pre-scaled, log2-domain bias table); different machine mapping:
+//
+//   * one CTA per SM, persistent over work items (window|stripe, head, group of NWG query tiles of 128 rows);
+//   * NWG softmax warpgroups share every K / V tile: K_t / V_t travel global -> shared ONCE per NWG*128 queries, as TMA
+//     boxes of the (B, H, W, C) tensors (a run of gcd(window width, shift) tokens stays contiguous under torch.roll);
+//   * S = Q K^T lands in TMEM; the softmax thread (one query row = one TMEM lane) turns it into P IN PLACE
+//     (tcgen05.ld -> exp2 -> tcgen05.st): P never touches shared memory and P V reads its A operand from TMEM;
+//   * O accumulates in TMEM across key tiles (tcgen05.mma accumulate); the running-max rescale is LAZY: O is touched
+//     by the softmax warps only when a row's maximum grew by more than 2^8 since its reference was fixed, which is
+//     rare after the first tile -- the 32-register output accumulator and its per-tile fold are gone;
+//   * while one warpgroup waits for its P V / next Q K^T round trip, the other NWG-1 keep the MUFU pipe busy -- the
+//     exp2 unit (16 / clk / SM) is the binding resource at head_dim 32, not the tensor pipe.
+//
+// Roles (threads = NWG * 128 + 64): warpgroups 0..NWG-1 softmax; warp 4 NWG = TMA producer, warp 4 NWG + 1 = single-thread
+// tcgen05.mma issuer.  (No setmaxnreg: the register pool of a CTA is what its own warps release, and 576 threads at 112
+// registers already use the whole file.)
+//
+// TMEM columns per warpgroup g: [96 g, 96 g + 64) = S_g (fp32) aliased by P_g (16-bit pairs in columns [0, 32));
+// [96 g + 64, 96 g + 96) = O_g.  The tensor pipe executes one thread's MMAs in issue order, so
+//   P V_g(t) ; Q K^T_g(t+1)   issued back to back is hazard free (the second overwrites what the first reads).
+#include <stdlib.h>
+
+#include "attn_tc.cuh"
+#include "grl_common.cuh"
+#include "ops_f32.h"
+#include "ops_tc.h"
+#include "tc_common.cuh"
+
+namespace grl {
+namespace tc {
+
+namespace {
+
+constexpr int kKT2 = 64;       // keys per tile
+constexpr int kStages2 = 4;    // K / V ring depth
+constexpr float kTau = 8.0f;   // lazy-rescale threshold (log2 units): P <= 2^8 stays far inside fp16 / bf16 range
+constexpr int kColsPerWg = 96;
+
+template <int NWG>
+struct A2Smem {
+  static constexpr int Q_BYTES = kQT * 64;
+  static constexpr int KV_BYTES = kKT2 * 64;
+  static constexpr int OFF_K = NWG * Q_BYTES;
+  static constexpr int OFF_V = OFF_K + kStages2 * KV_BYTES;
+  static constexpr int OFF_META = OFF_V + kStages2 * KV_BYTES;  // int koff[kStages2][KT], krid[kStages2][KT]
+  static constexpr int OFF_BAR = OFF_META + kStages2 * 2 * kKT2 * 4;
+  static constexpr int TOTAL = OFF_BAR + 256 + 1024;
+};
+
+struct A2Geom {
+  int bw_q, bw_k;   // tokens per TMA box
+  int n_qg;         // query groups (NWG * 128 rows) per window
+  int n_items;      // heads * B * windows * n_qg
+};
+
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
+      "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
+      "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// D[tmem] (+)= A[tmem] * B[smem]; issued by ONE thread.
+__device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, bool accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"((uint32_t)accumulate)
+      : "memory");
+}
+
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+
+struct Item {
+  int qg, h, bw, b, wr, wc, nact;
+};
+
+template <int NWG, int KW, int VAR>
+__global__ void __launch_bounds__(NWG * 128 + 64, 1)
+attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+             const __grid_constant__ CUtensorMap tmV, const AttnTcArgs a, const A2Geom tg) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  using S = A2Smem<NWG>;
+  constexpr int KT = kKT2;
+  uint8_t* Qs = smem;
+  uint8_t* Ks = smem + S::OFF_K;
+  uint8_t* Vs = smem + S::OFF_V;
+  int* koff_s = reinterpret_cast<int*>(smem + S::OFF_META);  // [kStages2][KT]
+  int* krid_s = koff_s + kStages2 * KT;                       // [kStages2][KT]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::OFF_BAR);
+  uint64_t* q_full = bars;                  // [NWG]  Q tile of warpgroup g landed            (TMA tx)
+  uint64_t* q_empty = q_full + 4;           // [NWG]  every Q K^T of the item that reads it is done  (tcgen05.commit)
+  uint64_t* bar_s = q_empty + 4;            // [NWG]  S_g(t) ready / O_g final                  (tcgen05.commit)
+  uint64_t* p_full = bar_s + 4;             // [NWG]  P_g(t) written to TMEM                     (4 warp arrivals)
+  uint64_t* kv_full = p_full + 4;           // [kStages2]  K_t, V_t landed                       (TMA tx)
+  uint64_t* kv_empty = kv_full + kStages2;  // [kStages2]  every MMA that reads the stage is done (tcgen05.commit)
+  uint64_t* meta_full = kv_empty + kStages2;  // [kStages2]  koff / rid of the stage written      (32 arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(meta_full + kStages2);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int wg = warp >> 2;
+  const int Nq = a.gq.wh * a.gq.ww, Nk = a.gk.wh * a.gk.ww;
+  const int nww = a.gq.W / a.gq.ww, nwh = a.gq.H / a.gq.wh;
+  const int nW = nwh * nww;
+  const int nBW = a.B * nW;
+  const int Wt = a.gq.ww + a.gk.ww - 1;
+  const int ntiles = (Nk + KT - 1) / KT;
+  constexpr uint32_t TMEM_COLS = (NWG * kColsPerWg <= 128) ? 128 : (NWG * kColsPerWg <= 256) ? 256 : 512;
+  constexpr int fmt = (VAR & 1) ? FMT_BF16 : FMT_F16;
+  constexpr bool ones = (VAR & 2) != 0;
+
+  if (tid == 0) {
+    for (int g = 0; g < NWG; ++g) {
+      mbar_init(&q_full[g], 1);
+      mbar_init(&q_empty[g], 1);
+      mbar_init(&bar_s[g], 1);
+      mbar_init(&p_full[g], 4);
+    }
+    for (int s = 0; s < kStages2; ++s) {
+      mbar_init(&kv_full[s], 1);
+      mbar_init(&kv_empty[s], 1);
+      mbar_init(&meta_full[s], 32);
+    }
+    mbar_init_fence();
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+  }
+  if (warp == 4 * NWG + 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  auto decode = [&](int item) {
+    Item it;
+    it.qg = item % tg.n_qg;
+    item /= tg.n_qg;
+    it.bw = item % nBW;
+    it.h = item / nBW;  // head slowest: CTAs that run concurrently read the same bias table
+    it.b = it.bw / nW;
+    const int w = it.bw - it.b * nW;
+    it.wr = w / nww;
+    it.wc = w - it.wr * nww;
+    const int left = Nq - it.qg * NWG * kQT;
+    it.nact = min(NWG, (left + kQT - 1) / kQT);
+    return it;
+  };
+
+  if (wg == NWG) {
+    if (warp == 4 * NWG) {
+      // =============================================================== TMA producer
+      // A run of `bw` consecutive tokens of one window row is contiguous in the (B, H, W, C) tensor even after the
+      // roll (bw divides gcd(window width, shift)), so it is ONE 4-D box (32 channels x bw x 1 x 1) that lands as bw
+      // rows of 64 bytes, 64-byte swizzled by the copy engine -- the layout the UMMA descriptors below expect.
+      auto tma_rows = [&](const CUtensorMap* map, const GrlGrid& g, const Item& it, int coff, uint8_t* dst, int n0,
+                          int cnt, int bw, uint64_t* bar) {
+        for (int s = lane; s * bw < cnt; s += 32) {
+          const int n = n0 + s * bw;
+          const int ih = n / g.ww, iw = n - ih * g.ww;
+          int y = it.wr * g.wh + ih + g.sh;
+          if (y >= g.H) y -= g.H;
+          int x = it.wc * g.ww + iw + g.sw;
+          if (x >= g.W) x -= g.W;
+          tma_load_4d(dst + s * bw * 64, map, bar, coff, x, y, it.b);
+        }
+      };
+      uint32_t kv_it = 0, q_cnt[NWG];
+#pragma unroll
+      for (int g = 0; g < NWG; ++g) q_cnt[g] = 0;
+      for (int item = blockIdx.x; item < tg.n_items; item += gridDim.x) {
+        const Item it = decode(item);
+        const bool need_mask = a.use_mask && (it.wr == nwh - 1 || it.wc == nww - 1);
+#pragma unroll
+        for (int g = 0; g < NWG; ++g) {
+          if (g < it.nact) {
+            mbar_wait(&q_empty[g], (q_cnt[g] & 1) ^ 1);
+            ++q_cnt[g];
+            const int q0 = (it.qg * NWG + g) * kQT;
+            const int cnt = min(kQT, Nq - q0);
+            if (lane == 0) mbar_expect_tx(&q_full[g], (uint32_t)cnt * 64u);
+            __syncwarp();
+            tma_rows(&tmQ, a.gq, it, a.q_off + it.h * kDP, Qs + g * S::Q_BYTES, q0, cnt, tg.bw_q, &q_full[g]);
+          }
+        }
+        for (int t = 0; t < ntiles; ++t, ++kv_it) {
+          const int st = kv_it % kStages2;
+          mbar_wait(&kv_empty[st], ((kv_it / kStages2) & 1) ^ 1);
+          const int k0 = t * KT, cnt = min(KT, Nk - k0);
+          uint8_t* kd = Ks + st * S::KV_BYTES;
+          uint8_t* vd = Vs + st * S::KV_BYTES;
+          if (cnt < KT && !a.v_dense) {  // ragged tile: V rows past Nk meet P == 0 and must be finite
+            for (int i = lane; i < (KT - cnt) * 4; i += 32) *reinterpret_cast<uint4*>(vd + cnt * 64 + i * 16) = make_uint4(0, 0, 0, 0);
+            fence_proxy_async_smem();
+          }
+          // koff / rid of the keys: read by the generic bias path (ragged tile, KW == 0) and by the shift mask
+          if (need_mask || KW == 0 || cnt < KT) {
+            for (int r = lane; r < KT; r += 32) {
+              const int kj = k0 + r;
+              const Tok tk = locate(a.gk, it.wr, it.wc, kj < Nk ? kj : 0);
+              koff_s[st * KT + r] = tk.ih * Wt + tk.iw;
+              krid_s[st * KT + r] = region_id(a.gk, tk.r, tk.c);
+            }
+          }
+          mbar_arrive(&meta_full[st]);
+          if (lane == 0) mbar_expect_tx(&kv_full[st], (uint32_t)(cnt + (a.v_dense ? KT : cnt)) * 64u);
+          __syncwarp();
+          tma_rows(&tmK, a.gk, it, a.k_off + it.h * kDP, kd, k0, cnt, tg.bw_k, &kv_full[st]);
+          if (a.v_dense) {  // (B_, heads, Nk, 32) rows: one 2-D box (rows past this head's Nk: next head / zero fill, P == 0)
+            if (lane == 0) tma_load_2d(vd, &tmV, &kv_full[st], 0, (int)(((long long)it.bw * a.heads + it.h) * Nk + k0));
+          } else {
+            tma_rows(&tmV, a.gk, it, a.v_off + it.h * kDP, vd, k0, cnt, tg.bw_k, &kv_full[st]);
+          }
+        }
+      }
+    } else if (warp == 4 * NWG + 1) {
+      // =============================================================== MMA issuer (one thread)
+      const uint32_t idesc_qk = umma_idesc(kQT, KT, fmt, 0, 0);
+      const uint32_t idesc_pv = umma_idesc(kQT, kDP, fmt, 0, 1);
+      uint32_t kv_it = 0, q_cnt[NWG], p_cnt[NWG];
+#pragma unroll
+      for (int g = 0; g < NWG; ++g) q_cnt[g] = 0, p_cnt[g] = 0;
+      auto issue_qk = [&](int g, int st, bool last) {
+        const uint32_t q_sa = smem_u32(Qs + g * S::Q_BYTES), k_sa = smem_u32(Ks + st * S::KV_BYTES);
+#pragma unroll
+        for (int k = 0; k < kDP / 16; ++k)
+          umma_ss(tmem + g * kColsPerWg, umma_desc(q_sa + k * 32, 16, 512, SWZ_64B), umma_desc(k_sa + k * 32, 16, 512, SWZ_64B),
+                  idesc_qk, k != 0);
+        if (last) umma_commit(&q_empty[g]);
+      };
+      for (int item = blockIdx.x; item < tg.n_items; item += gridDim.x) {
+        const Item it = decode(item);
+        {
+          const int st = kv_it % kStages2;
+          mbar_wait(&kv_full[st], (kv_it / kStages2) & 1);
+#pragma unroll
+          for (int g = 0; g < NWG; ++g) {
+            if (g < it.nact) {
+              mbar_wait(&q_full[g], q_cnt[g] & 1);
+              ++q_cnt[g];
+              if (lane == 0) {
+                tcgen05_fence_after();
+                issue_qk(g, st, ntiles == 1);
+                umma_commit(&bar_s[g]);
+              }
+              __syncwarp();
+            }
+          }
+        }
+        for (int t = 0; t < ntiles; ++t, ++kv_it) {
+          const int st = kv_it % kStages2, st1 = (kv_it + 1) % kStages2;
+          if (t + 1 < ntiles) mbar_wait(&kv_full[st1], ((kv_it + 1) / kStages2) & 1);
+#pragma unroll
+          for (int g = 0; g < NWG; ++g) {
+            if (g < it.nact) {
+              mbar_wait(&p_full[g], p_cnt[g] & 1);
+              ++p_cnt[g];
+              if (lane == 0) {
+                tcgen05_fence_after();
+                const uint32_t v_sa = smem_u32(Vs + st * S::KV_BYTES);
+                const uint32_t p_ta = tmem + g * kColsPerWg;
+#pragma unroll
+                for (int k = 0; k < KT / 16; ++k)
+                  umma_ts(p_ta + 64, p_ta + k * 8, umma_desc(v_sa + k * 1024, 16, 512, SWZ_64B), idesc_pv, (t | k) != 0);
+                if (t + 1 < ntiles) issue_qk(g, st1, t + 2 == ntiles);
+                umma_commit(&bar_s[g]);
+              }
+              __syncwarp();
+            }
+          }
+          if (lane == 0) umma_commit(&kv_empty[st]);
+          __syncwarp();
+        }
+      }
+      // every commit has arrived before the CTA's shared memory goes away
+      if (kv_it > 0) {
+        const uint32_t last = kv_it - 1;
+        mbar_wait(&kv_empty[last % kStages2], (last / kStages2) & 1);
+      }
+    }
+  } else {
+    // =============================================================== softmax warpgroups: thread = query row
+    const int row = tid & 127;
+    const uint32_t ts = tmem + ((uint32_t)((warp & 3) * 32) << 16) + wg * kColsPerWg;  // S / P columns of this row
+    const uint32_t to = ts + 64;                                                         // O columns
+    uint32_t s_cnt = 0, kv_it = 0;
+    for (int item = blockIdx.x; item < tg.n_items; item += gridDim.x) {
+      const Item it = decode(item);
+      if (wg >= it.nact) {
+        kv_it += ntiles;
+        continue;
+      }
+      const int qi = (it.qg * NWG + wg) * kQT + row;
+      const bool q_ok = qi < Nq;
+      const Tok tq = locate(a.gq, it.wr, it.wc, q_ok ? qi : it.qg * NWG * kQT);
+      const float* bias_h = a.bias + (size_t)it.h * 4 * a.rows_pad;
+      const int base_i = (tq.ih + a.gk.wh - 1) * Wt + tq.iw + a.gk.ww - 1;
+      const int q_rid = region_id(a.gq, tq.r, tq.c);
+      const bool need_mask = a.use_mask && (it.wr == nwh - 1 || it.wc == nww - 1);
+      float m_ref = 0.f, l_run = 0.f;
+
+      for (int t = 0; t < ntiles; ++t, ++kv_it) {
+        const int k0 = t * KT, st = kv_it % kStages2;
+        const bool full_tile = (KW > 0) && (k0 + KT <= Nk);
+        // ---- x = bias - m_ref first: these loads and adds do not depend on S and run while Q K^T is in flight
+        float x[KT];
+        if (full_tile) {
+          constexpr int KWS = KW > 0 ? KW : 4;
+          constexpr int RW = (KWS >= 32) ? 32 : KWS;  // consecutive keys of one key row
+#pragma unroll
+          for (int r0 = 0; r0 < KT; r0 += RW) {
+            const int kj = k0 + r0;  // first key of the run (CTA-uniform, multiple of 4)
+            const int s0 = base_i - ((kj / KWS) * Wt + (kj % KWS)) - 3;  // table index of key kj + 3
+            const int cpy = (-s0) & 3;
+            const float4* bp = reinterpret_cast<const float4*>(bias_h + (size_t)cpy * a.rows_pad + (s0 + cpy));
+#pragma unroll
+            for (int qd = 0; qd < RW / 4; ++qd) {
+              const float4 bb = __ldg(bp - qd);
+              const int j = r0 + 4 * qd;
+              x[j + 0] = bb.w - m_ref, x[j + 1] = bb.z - m_ref, x[j + 2] = bb.y - m_ref, x[j + 3] = bb.x - m_ref;
+            }
+          }
+        } else {
+          mbar_wait(&meta_full[st], (kv_it / kStages2) & 1);
+#pragma unroll
+          for (int j = 0; j < KT; ++j) x[j] = __ldg(bias_h + base_i - koff_s[st * KT + j]) - m_ref;
+        }
+        if (need_mask) {
+          if (full_tile) mbar_wait(&meta_full[st], (kv_it / kStages2) & 1);
+#pragma unroll
+          for (int j = 0; j < KT; ++j)
+            if (krid_s[st * KT + j] != q_rid) x[j] += kMaskLog2;
+        }
+        // ---- S_t
+        mbar_wait(&bar_s[wg], s_cnt & 1);
+        ++s_cnt;
+        tcgen05_fence_after();
+#pragma unroll
+        for (int c0 = 0; c0 < KT; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld32(ts + c0, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) x[c0 + j] += __uint_as_float(v[j]);
+        }
+        if (k0 + KT > Nk) {  // after the add: K rows past Nk are stale shared memory, S there may be anything
+#pragma unroll
+          for (int j = 0; j < KT; ++j)
+            if (k0 + j >= Nk) x[j] = -INFINITY;
+        }
+        float mx0 = fmax3(x[0], x[1], x[2]), mx1 = fmax3(x[3], x[4], x[5]);
+#pragma unroll
+        for (int j = 6; j + 3 < KT; j += 4) {
+          mx0 = fmax3(mx0, x[j], x[j + 1]);
+          mx1 = fmax3(mx1, x[j + 2], x[j + 3]);
+        }
+        const float mx = fmax3(mx0, mx1, fmaxf(x[KT - 2], x[KT - 1]));
+        // ---- lazy rescale: move the reference only when a row outgrew it by 2^kTau (always on the first tile)
+        const bool first = (t == 0);
+        if (__any_sync(0xffffffffu, first || mx > kTau)) {
+          float delta = first ? mx : fmaxf(mx, 0.f);
+          if (!(fabsf(delta) < 1e30f)) delta = 0.f;  // rows of a partial query tile hold garbage
+          m_ref += delta;
+#pragma unroll
+          for (int j = 0; j < KT; ++j) x[j] -= delta;
+          if (!first) {  // O_g holds P V of tiles < t (complete: bar_s(t) covers every earlier MMA of the issuer)
+            const float sc = ex2(-delta);
+            uint32_t v[32];
+            tmem_ld32(to, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int e = 0; e < kDP; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) * sc);
+            tmem_st32(to, v);
+            l_run *= sc;
+          }
+        }
+        // ---- P_t = exp2(x) -> 16-bit pairs -> TMEM (over S_t)
+        uint32_t pk[32];
+        float ps0 = 0.f, ps1 = 0.f;
+#pragma unroll
+        for (int c = 0; c < KT / 2; ++c) {
+          const float p0 = ex2(x[2 * c]), p1 = ex2(x[2 * c + 1]);
+          if (!ones) ps0 += p0, ps1 += p1;
+          pk[c] = (fmt == FMT_BF16) ? pack_bf16(p0, p1) : pack_f16(p0, p1);
+        }
+        if (!ones) l_run += ps0 + ps1;
+        tmem_st32(ts, pk);
+        tmem_st_wait();
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[wg]);
+      }
+      // ---- epilogue: O_g final
+      mbar_wait(&bar_s[wg], s_cnt & 1);
+      ++s_cnt;
+      tcgen05_fence_after();
+      {
+        uint32_t v[32];
+        tmem_ld32(to, v);
+        tmem_ld_wait();
+        if (q_ok) {
+          const float inv = 1.0f / (ones ? __uint_as_float(v[kDP - 1]) : l_run);
+          const long long q_tok = (long long)(it.b * a.gq.H + tq.y) * a.gq.W + tq.x;
+          __nv_bfloat16* dst = a.o_dense ? a.out + (((long long)it.bw * a.heads + it.h) * Nq + qi) * kDP
+                                         : a.out + q_tok * a.ldo + a.o_off + it.h * kDP;
+#pragma unroll
+          for (int e = 0; e < kDP; e += 8) {
+            float o[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o[i] = __uint_as_float(v[e + i]) * inv;
+            *reinterpret_cast<uint4*>(dst + e) = make_uint4(pack16(o[0], o[1], fmt), pack16(o[2], o[3], fmt),
+                                                            pack16(o[4], o[5], fmt), pack16(o[6], o[7], fmt));
+          }
+        }
+      }
+      tcgen05_fence_before();
+    }
+  }
+  __syncthreads();
+  if (warp == 4 * NWG + 1) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem, TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------------
+// Tokens per box for a window of width ww rolled by sw: the largest power of two <= 64 dividing gcd(ww, sw) (ww if the
+// grid is not rolled horizontally).  0 = no usable box (runs shorter than 8 tokens = 512 bytes, the 64-byte-swizzle repeat).
+int box_tokens2(const GrlGrid& g) {
+  int d = g.ww;
+  if (g.sw > 0) {
+    int x = g.ww, y = g.sw;
+    while (y) {
+      const int t = x % y;
+      x = y, y = t;
+    }
+    d = x;
+  }
+  int bw = 64;
+  while (bw > 1 && d % bw) bw >>= 1;
+  return bw >= 8 ? bw : 0;
+}
+
+int make_token_map2(CUtensorMap* m, const void* base, long long ld, const GrlGrid& g, int B, int bw) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) return fail(GRL_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  const cuuint64_t dims[4] = {(cuuint64_t)ld, (cuuint64_t)g.W, (cuuint64_t)g.H, (cuuint64_t)B};
+  const cuuint64_t str[3] = {(cuuint64_t)ld * 2, (cuuint64_t)g.W * ld * 2, (cuuint64_t)g.H * g.W * ld * 2};
+  const cuuint32_t box[4] = {(cuuint32_t)kDP, (cuuint32_t)bw, 1, 1};
+  const cuuint32_t ones[4] = {1, 1, 1, 1};
+  const CUresult rc = fn(m, CU_TENSOR_MAP_DATA_TYPE_UINT16, 4, const_cast<void*>(base), dims, str, box, ones,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (rc != CUDA_SUCCESS) return fail(GRL_ERR_CUDA, "cuTensorMapEncodeTiled (attention tokens) failed with CUresult %d", (int)rc);
+  return GRL_OK;
+}
+
+int make_dense_map2(CUtensorMap* m, const void* base, long long rows, int box_rows) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) return fail(GRL_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  const cuuint64_t dims[2] = {(cuuint64_t)kDP, (cuuint64_t)rows};
+  const cuuint64_t str[1] = {(cuuint64_t)kDP * 2};
+  const cuuint32_t box[2] = {(cuuint32_t)kDP, (cuuint32_t)box_rows};
+  const cuuint32_t ones[2] = {1, 1};
+  const CUresult rc = fn(m, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, const_cast<void*>(base), dims, str, box, ones,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (rc != CUDA_SUCCESS) return fail(GRL_ERR_CUDA, "cuTensorMapEncodeTiled (dense V) failed with CUresult %d", (int)rc);
+  return GRL_OK;
+}
+
+int sm_count() {
+  static int n[16] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return 148;
+  if (n[dev] == 0) {
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+    n[dev] = v;
+  }
+  return n[dev];
+}
+
+template <int NWG, int KW, int VAR>
+int launch2_var(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnTcArgs& a, A2Geom tg,
+                cudaStream_t st) {
+  auto kern = attn2_kernel<NWG, KW, VAR>;
+  static bool configured[16] = {false};
+  int dev = 0;
+  GRL_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 16 || !configured[dev]) {
+    GRL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, A2Smem<NWG>::TOTAL));
+    if (dev >= 0 && dev < 16) configured[dev] = true;
+  }
+  const int Nq = a.gq.wh * a.gq.ww;
+  tg.n_qg = ceil_div(Nq, NWG * kQT);
+  const long long items = (long long)a.heads * a.B * (a.gq.H / a.gq.wh) * (a.gq.W / a.gq.ww) * tg.n_qg;
+  GRL_REQUIRE(items < (1ll << 31), "attn2: too many work items");
+  tg.n_items = (int)items;
+  const unsigned grid = (unsigned)min((long long)sm_count(), items);
+  kern<<<grid, NWG * 128 + 64, A2Smem<NWG>::TOTAL, st>>>(tq, tk, tv, a, tg);
+  GRL_LAUNCH_CHECK("attn2_kernel");
+  return GRL_OK;
+}
+
+template <int NWG, int KW>
+int launch2_kw(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnTcArgs& a, const A2Geom& tg,
+               cudaStream_t st) {
+  switch ((a.fmt == FMT_BF16 ? 1 : 0) | (a.ones_col ? 2 : 0)) {
+    case 0: return launch2_var<NWG, KW, 0>(tq, tk, tv, a, tg, st);
+    case 1: return launch2_var<NWG, KW, 1>(tq, tk, tv, a, tg, st);
+    case 2: return launch2_var<NWG, KW, 2>(tq, tk, tv, a, tg, st);
+    default: return launch2_var<NWG, KW, 3>(tq, tk, tv, a, tg, st);
+  }
+}
+
+template <int NWG>
+int launch2_nwg(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnTcArgs& a, const A2Geom& tg,
+                cudaStream_t st) {
+  switch (a.gk.ww) {
+    case 16: return launch2_kw<NWG, 16>(tq, tk, tv, a, tg, st);
+    case 32: return launch2_kw<NWG, 32>(tq, tk, tv, a, tg, st);
+    case 64: return launch2_kw<NWG, 64>(tq, tk, tv, a, tg, st);
+    case 128: return launch2_kw<NWG, 128>(tq, tk, tv, a, tg, st);
+    default: return launch2_kw<NWG, 0>(tq, tk, tv, a, tg, st);
+  }
+}
+
+}  // namespace
+
+// Returns GRL_OK after launching, a negative error, or +1 when this geometry cannot be expressed as TMA boxes (the
+// caller then launches the gather kernel of attn_tc.cu).  Arguments already validated by launch_attn_tc.
+int launch_attn2(const AttnTcArgs& a, cudaStream_t st) {
+  A2Geom tg;
+  tg.bw_q = box_tokens2(a.gq);
+  tg.bw_k = box_tokens2(a.gk);
+  tg.n_qg = tg.n_items = 0;
+  if (tg.bw_q == 0 || tg.bw_k == 0) return 1;
+  if (a.gq.W < tg.bw_q || a.gk.W < tg.bw_k) return 1;
+  if ((reinterpret_cast<uintptr_t>(a.q) | reinterpret_cast<uintptr_t>(a.k) | reinterpret_cast<uintptr_t>(a.v)) & 15) return 1;
+  CUtensorMap tq, tk, tv;
+  int rc;
+  if ((rc = make_token_map2(&tq, a.q, a.ldq, a.gq, a.B, tg.bw_q)) != GRL_OK) return rc;
+  if ((rc = make_token_map2(&tk, a.k, a.ldk, a.gk, a.B, tg.bw_k)) != GRL_OK) return rc;
+  if (a.v_dense) {
+    const long long rows = (long long)a.B * (a.gk.H / a.gk.wh) * (a.gk.W / a.gk.ww) * a.heads * a.gk.wh * a.gk.ww;
+    if (rows < kKT2) return 1;  // the dense-V box is 64 rows: keep it inside the tensor
+    if ((rc = make_dense_map2(&tv, a.v, rows, kKT2)) != GRL_OK) return rc;
+  } else {
+    if ((rc = make_token_map2(&tv, a.v, a.ldv, a.gk, a.B, tg.bw_k)) != GRL_OK) return rc;
+  }
+  return launch2_nwg<3>(tq, tk, tv, a, tg, st);
+}
+
+}  // namespace tc
+}  // namespace grl

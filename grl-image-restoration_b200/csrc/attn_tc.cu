@@ -439,10 +439,10 @@ int attn_variant(int set) {
   if (variant < 0) {
     const char* e = getenv("GRL_ATTN_SPLIT");
     const int v = e ? atoi(e) : 0;
-    variant = (v >= 1 && v <= 4) ? v : 0;
+    variant = (v >= 1 && v <= 5) ? v : 0;
   }
   const int prev = variant;
-  if (set >= 0 && set <= 4) variant = set;
+  if (set >= 0 && set <= 5) variant = set;
   return prev;
 }
 
@@ -463,6 +463,10 @@ int launch_attn_tc(const AttnTcArgs& a, cudaStream_t st) {
   if (split == 1 || split == 2) return launch_attn_tc_split(a, (unsigned)nblk, split, st);
   if (split == 3 || split == 4) {  // TMA producer where the geometry allows it, else fall through to the gather kernel
     const int rc = launch_attn_tc_tma(a, (unsigned)nblk, split == 4, st);
+    if (rc <= 0) return rc;
+  }
+  if (split == 5) {  // persistent TMEM-resident kernel (attn2.cu) where the geometry allows it
+    const int rc = launch_attn2(a, st);
     if (rc <= 0) return rc;
   }
   // 64 keys per tile, 3 CTAs / SM (32- and 128-key tiles were measured slower: profiles/r1_tc_path_final.md)

@@ -85,6 +85,9 @@ int launch_attn_tc_split(const AttnTcArgs& a, unsigned nblk, int mode, cudaStrea
 // the geometry has no TMA box form
 int launch_attn_tc_tma(const AttnTcArgs& a, unsigned nblk, bool staged_bias, cudaStream_t st);
 int attn_tma_box_tokens(const GrlGrid& g);
+// persistent warp-specialised kernel (attn2.cu): P and O in TMEM, NWG query tiles share each K / V tile; returns +1 when the
+// geometry has no TMA box form
+int launch_attn2(const AttnTcArgs& a, cudaStream_t st);
 
 }  // namespace tc
 }  // namespace grl

@@ -1,7 +1,8 @@
 """TEST INFRASTRUCTURE ONLY. Imports the UNMODIFIED reference model from /root/reference.
 
-Only usable in the build container (the GPU box has no /root/reference).  Used by
-oracle/make_golden.py to pin the oracle restatement and to write tests/golden/*.npz.
+Used by oracle/make_golden*.py (build container, /root/reference) to pin the oracle restatement and to write
+tests/golden/*.npz, and by bench.py's reference arm / cpu_baseline leg (GPU box: the copy staged under oracle/_ref by
+oracle/make_ref.py).
 
 The reference's model files need three absent third-party packages for a handful of helpers
 (SURVEY.md section 8c / Appendix E); we register minimal stand-ins in sys.modules:
@@ -16,7 +17,19 @@ import types
 
 import torch
 
-REF_ROOT = os.environ.get("GRL_REFERENCE_ROOT", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _pick_root():
+    """/root/reference in the build container; oracle/_ref (staged byte for byte by oracle/make_ref.py, git-ignored,
+    shipped with the gpurun snapshot) on the GPU box."""
+    for cand in (os.environ.get("GRL_REFERENCE_ROOT"), "/root/reference", os.path.join(_HERE, "_ref")):
+        if cand and os.path.isfile(os.path.join(cand, "models", "networks", "grl.py")):
+            return cand
+    return os.environ.get("GRL_REFERENCE_ROOT", "/root/reference")
+
+
+REF_ROOT = _pick_root()
 
 
 def reference_available():

@@ -61,3 +61,45 @@ def test_psnr_matches_oracle(pkg, oracle, golden_loader):
     g = golden_loader("model_micro_cab_x2.npz")
     assert torch.equal(metrics.psnr(g["psnr/a"], g["psnr/b"], 4), g["psnr/value_border4"])
     assert torch.equal(metrics.psnr(g["psnr/a"], g["psnr/b"], 0), oracle.psnr(g["psnr/a"], g["psnr/b"], 0))
+
+
+class _FakeModel:
+    """Stand-in for GRL on the CPU: a per-tile function with a tile-global term (like the CAB pool), x2 upscale."""
+    upscale, out_channels = 2, 3
+
+    def __call__(self, patches):
+        up = torch.nn.functional.interpolate(patches, scale_factor=2, mode="nearest")
+        return up * 0.5 + patches.mean(dim=(1, 2, 3), keepdim=True)
+
+
+def _tile_worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    from _pkgload import load_package
+
+    load_package()
+    from grl_image_restoration_b200 import tiling
+
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    x = torch.rand(1, 3, 72, 128, generator=torch.Generator().manual_seed(3))  # 2 x 3 = 6 tiles of 48 (overlap 8)
+    y = tiling.forward_tile_sharded(_FakeModel(), x, 48, 8, max_batch=2)
+    torch.save(y, out + f".{rank}")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_forward_tile_sharded_world2_gloo(pkg, tmp_path):
+    """cfg5's N>1 path: tiles of one frame round-robin over ranks, all-gather, E / W on every rank == single-process."""
+    from grl_image_restoration_b200 import tiling
+
+    out = str(tmp_path / "tiles.pt")
+    port = 31500 + os.getpid() % 2000
+    mp.spawn(_tile_worker, args=(2, port, out), nprocs=2, join=True)
+    x = torch.rand(1, 3, 72, 128, generator=torch.Generator().manual_seed(3))
+    ref = tiling.forward_tile(_FakeModel(), x, 48, 8, max_batch=4)
+    assert tiling.tile_origins(72, 48, 8) == [0, 24] and tiling.tile_origins(128, 48, 8) == [0, 40, 80]
+    assert tiling.shard_tiles(6, 0, 2) == [0, 2, 4] and tiling.shard_tiles(6, 1, 2) == [1, 3, 5]
+    for r in range(2):
+        y = torch.load(out + f".{r}")
+        assert y.shape == (1, 3, 144, 256)
+        assert torch.allclose(y, ref, atol=1e-6, rtol=0)
