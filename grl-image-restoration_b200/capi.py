@@ -124,5 +124,11 @@ def stream():
 
 
 def require_device(t):
+    """The C ABI launches on the CURRENT device's current stream (one process per GPU, as under DDP / torchrun).  A
+    tensor living on another device of the same process would be launched with foreign pointers: refuse it with a
+    clear message instead (wrap the call in `with torch.cuda.device(t.device):`)."""
     if not t.is_cuda:
         raise RuntimeError("grl_b200: input is not on a CUDA device; the B200 kernels have no CPU fallback")
+    if t.device.index != torch.cuda.current_device():
+        raise RuntimeError(f"grl_b200: tensor on cuda:{t.device.index} but the current device is cuda:{torch.cuda.current_device()}; "
+                           f"call torch.cuda.set_device / use `with torch.cuda.device(...)` (kernels launch on the current device)")

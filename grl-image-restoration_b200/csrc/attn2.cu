@@ -46,7 +46,7 @@ struct A2Smem {
   static constexpr int OFF_V = OFF_K + kStages2 * KV_BYTES;
   static constexpr int OFF_META = OFF_V + kStages2 * KV_BYTES;  // int koff[kStages2][KT], krid[kStages2][KT]
   static constexpr int OFF_BAR = OFF_META + kStages2 * 2 * kKT2 * 4;
-  static constexpr int TOTAL = OFF_BAR + 256 + 1024;
+  static constexpr int TOTAL = OFF_BAR + 512 + 1024;
 };
 
 struct A2Geom {
@@ -78,6 +78,30 @@ __device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64
       : "memory");
 }
 
+// Lean mbarrier wait: mbarrier.try_wait suspends the thread in hardware until the phase completes or a system time limit
+// passes, so the retry loop is two instructions; a wall-clock bound (checked every 4096 retries) turns a protocol bug into
+// a trap instead of a hung GPU.
+__device__ __forceinline__ void mbar_wait2(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  int spins = 0;
+  long long t0 = 0;
+  for (;;) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (ok) return;
+    if ((++spins & 4095) == 0) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000ll) __trap();
+    }
+  }
+}
+
 __device__ __forceinline__ float fmax3(float a, float b, float c) {
   float d;
   asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
@@ -104,9 +128,11 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::OFF_BAR);
   uint64_t* q_full = bars;                  // [NWG]  Q tile of warpgroup g landed            (TMA tx)
   uint64_t* q_empty = q_full + 4;           // [NWG]  every Q K^T of the item that reads it is done  (tcgen05.commit)
-  uint64_t* bar_s = q_empty + 4;            // [NWG]  S_g(t) ready / O_g final                  (tcgen05.commit)
+  uint64_t* bar_s = q_empty + 4;            // [NWG]  S_g(t) ready                               (tcgen05.commit)
   uint64_t* p_full = bar_s + 4;             // [NWG]  P_g(t) written to TMEM                     (4 warp arrivals)
-  uint64_t* kv_full = p_full + 4;           // [kStages2]  K_t, V_t landed                       (TMA tx)
+  uint64_t* o_full = p_full + 4;            // [NWG]  O_g of the item final (own barrier: bar_s would otherwise complete
+                                            //        twice -- final O, next item's S_0 -- without a p_full in between)
+  uint64_t* kv_full = o_full + 4;           // [kStages2]  K_t, V_t landed                       (TMA tx)
   uint64_t* kv_empty = kv_full + kStages2;  // [kStages2]  every MMA that reads the stage is done (tcgen05.commit)
   uint64_t* meta_full = kv_empty + kStages2;  // [kStages2]  koff / rid of the stage written      (32 arrivals)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(meta_full + kStages2);
@@ -129,6 +155,7 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
       mbar_init(&q_empty[g], 1);
       mbar_init(&bar_s[g], 1);
       mbar_init(&p_full[g], 4);
+      mbar_init(&o_full[g], 1);
     }
     for (int s = 0; s < kStages2; ++s) {
       mbar_init(&kv_full[s], 1);
@@ -188,7 +215,7 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
 #pragma unroll
         for (int g = 0; g < NWG; ++g) {
           if (g < it.nact) {
-            mbar_wait(&q_empty[g], (q_cnt[g] & 1) ^ 1);
+            mbar_wait2(&q_empty[g], (q_cnt[g] & 1) ^ 1);
             ++q_cnt[g];
             const int q0 = (it.qg * NWG + g) * kQT;
             const int cnt = min(kQT, Nq - q0);
@@ -199,7 +226,7 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
         }
         for (int t = 0; t < ntiles; ++t, ++kv_it) {
           const int st = kv_it % kStages2;
-          mbar_wait(&kv_empty[st], ((kv_it / kStages2) & 1) ^ 1);
+          mbar_wait2(&kv_empty[st], ((kv_it / kStages2) & 1) ^ 1);
           const int k0 = t * KT, cnt = min(KT, Nk - k0);
           uint8_t* kd = Ks + st * S::KV_BYTES;
           uint8_t* vd = Vs + st * S::KV_BYTES;
@@ -246,11 +273,11 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
         const Item it = decode(item);
         {
           const int st = kv_it % kStages2;
-          mbar_wait(&kv_full[st], (kv_it / kStages2) & 1);
+          mbar_wait2(&kv_full[st], (kv_it / kStages2) & 1);
 #pragma unroll
           for (int g = 0; g < NWG; ++g) {
             if (g < it.nact) {
-              mbar_wait(&q_full[g], q_cnt[g] & 1);
+              mbar_wait2(&q_full[g], q_cnt[g] & 1);
               ++q_cnt[g];
               if (lane == 0) {
                 tcgen05_fence_after();
@@ -263,11 +290,11 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
         }
         for (int t = 0; t < ntiles; ++t, ++kv_it) {
           const int st = kv_it % kStages2, st1 = (kv_it + 1) % kStages2;
-          if (t + 1 < ntiles) mbar_wait(&kv_full[st1], ((kv_it + 1) / kStages2) & 1);
+          if (t + 1 < ntiles) mbar_wait2(&kv_full[st1], ((kv_it + 1) / kStages2) & 1);
 #pragma unroll
           for (int g = 0; g < NWG; ++g) {
             if (g < it.nact) {
-              mbar_wait(&p_full[g], p_cnt[g] & 1);
+              mbar_wait2(&p_full[g], p_cnt[g] & 1);
               ++p_cnt[g];
               if (lane == 0) {
                 tcgen05_fence_after();
@@ -276,8 +303,12 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
 #pragma unroll
                 for (int k = 0; k < KT / 16; ++k)
                   umma_ts(p_ta + 64, p_ta + k * 8, umma_desc(v_sa + k * 1024, 16, 512, SWZ_64B), idesc_pv, (t | k) != 0);
-                if (t + 1 < ntiles) issue_qk(g, st1, t + 2 == ntiles);
-                umma_commit(&bar_s[g]);
+                if (t + 1 < ntiles) {
+                  issue_qk(g, st1, t + 2 == ntiles);
+                  umma_commit(&bar_s[g]);
+                } else {
+                  umma_commit(&o_full[g]);
+                }
               }
               __syncwarp();
             }
@@ -289,7 +320,7 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
       // every commit has arrived before the CTA's shared memory goes away
       if (kv_it > 0) {
         const uint32_t last = kv_it - 1;
-        mbar_wait(&kv_empty[last % kStages2], (last / kStages2) & 1);
+        mbar_wait2(&kv_empty[last % kStages2], (last / kStages2) & 1);
       }
     }
   } else {
@@ -297,7 +328,7 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
     const int row = tid & 127;
     const uint32_t ts = tmem + ((uint32_t)((warp & 3) * 32) << 16) + wg * kColsPerWg;  // S / P columns of this row
     const uint32_t to = ts + 64;                                                         // O columns
-    uint32_t s_cnt = 0, kv_it = 0;
+    uint32_t s_cnt = 0, o_cnt = 0, kv_it = 0;
     for (int item = blockIdx.x; item < tg.n_items; item += gridDim.x) {
       const Item it = decode(item);
       if (wg >= it.nact) {
@@ -310,13 +341,22 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
       const float* bias_h = a.bias + (size_t)it.h * 4 * a.rows_pad;
       const int base_i = (tq.ih + a.gk.wh - 1) * Wt + tq.iw + a.gk.ww - 1;
       const int q_rid = region_id(a.gq, tq.r, tq.c);
-      const bool need_mask = a.use_mask && (it.wr == nwh - 1 || it.wc == nww - 1);
+      // shift mask (ops.py:112-157): only windows of the last row / column carry one.  Region id of key (kh, kw) of this
+      // window = 3 (a1 + [a1 & kh >= wh - sh]) + (b1 + [b1 & kw >= ww - sw])  (grl_geometry.h region_id in window coordinates)
+      const bool a1 = it.wr == nwh - 1, b1 = it.wc == nww - 1;
+      const bool need_mask = a.use_mask && (a1 || b1);
+      const int kh_th = (a1 && a.gk.sh > 0) ? a.gk.wh - a.gk.sh : 0x7fffffff;  // first key row of the wrapped region
+      const int kw_th = (b1 && a.gk.sw > 0) ? a.gk.ww - a.gk.sw : 0x7fffffff;  // first key column of the wrapped region
+      // closed-form masks need every aligned group of 4 keys to lie on one side of kw_th
+      const bool mask_fast = (KW > 0) && (a.gk.sw == 0 || ((a.gk.ww - a.gk.sw) & 3) == 0);
       float m_ref = 0.f, l_run = 0.f;
 
       for (int t = 0; t < ntiles; ++t, ++kv_it) {
         const int k0 = t * KT, st = kv_it % kStages2;
         const bool full_tile = (KW > 0) && (k0 + KT <= Nk);
-        // ---- x = bias - m_ref first: these loads and adds do not depend on S and run while Q K^T is in flight
+        // ---- x = bias (+ mask) - m_ref first: these loads and adds do not depend on S and run while Q K^T is in flight.
+        // Nothing here may touch the per-stage metadata: a warpgroup that sat out the previous item is a whole item
+        // ahead of the producer, and an mbarrier parity wait only orders phases that are at most one apart.
         float x[KT];
         if (full_tile) {
           constexpr int KWS = KW > 0 ? KW : 4;
@@ -324,31 +364,35 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
 #pragma unroll
           for (int r0 = 0; r0 < KT; r0 += RW) {
             const int kj = k0 + r0;  // first key of the run (CTA-uniform, multiple of 4)
-            const int s0 = base_i - ((kj / KWS) * Wt + (kj % KWS)) - 3;  // table index of key kj + 3
+            const int kh = kj / KWS, kw0 = kj % KWS;
+            const int s0 = base_i - (kh * Wt + kw0) - 3;  // table index of key kj + 3
             const int cpy = (-s0) & 3;
             const float4* bp = reinterpret_cast<const float4*>(bias_h + (size_t)cpy * a.rows_pad + (s0 + cpy));
+            float off_lo = m_ref, off_hi = m_ref;
+            if (need_mask && mask_fast) {
+              const int rid_lo = 3 * ((int)a1 + (int)(kh >= kh_th)) + (int)b1;
+              off_lo = (rid_lo != q_rid) ? m_ref - kMaskLog2 : m_ref;
+              off_hi = (rid_lo + 1 != q_rid) ? m_ref - kMaskLog2 : m_ref;
+            }
 #pragma unroll
             for (int qd = 0; qd < RW / 4; ++qd) {
               const float4 bb = __ldg(bp - qd);
               const int j = r0 + 4 * qd;
-              x[j + 0] = bb.w - m_ref, x[j + 1] = bb.z - m_ref, x[j + 2] = bb.y - m_ref, x[j + 3] = bb.x - m_ref;
+              const float off = (kw0 + 4 * qd >= kw_th) ? off_hi : off_lo;
+              x[j + 0] = bb.w - off, x[j + 1] = bb.z - off, x[j + 2] = bb.y - off, x[j + 3] = bb.x - off;
             }
           }
-        } else {
-          mbar_wait(&meta_full[st], (kv_it / kStages2) & 1);
+        }
+        // ---- S_t
+        mbar_wait2(&bar_s[wg], s_cnt & 1);
+        ++s_cnt;
+        tcgen05_fence_after();
+        const bool meta_mask = need_mask && !(full_tile && mask_fast);
+        if (!full_tile || meta_mask) mbar_wait2(&meta_full[st], (kv_it / kStages2) & 1);  // S_t ready => this fill is the current one
+        if (!full_tile) {
 #pragma unroll
           for (int j = 0; j < KT; ++j) x[j] = __ldg(bias_h + base_i - koff_s[st * KT + j]) - m_ref;
         }
-        if (need_mask) {
-          if (full_tile) mbar_wait(&meta_full[st], (kv_it / kStages2) & 1);
-#pragma unroll
-          for (int j = 0; j < KT; ++j)
-            if (krid_s[st * KT + j] != q_rid) x[j] += kMaskLog2;
-        }
-        // ---- S_t
-        mbar_wait(&bar_s[wg], s_cnt & 1);
-        ++s_cnt;
-        tcgen05_fence_after();
 #pragma unroll
         for (int c0 = 0; c0 < KT; c0 += 32) {
           uint32_t v[32];
@@ -356,6 +400,11 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 32; ++j) x[c0 + j] += __uint_as_float(v[j]);
+        }
+        if (meta_mask) {
+#pragma unroll
+          for (int j = 0; j < KT; ++j)
+            if (krid_s[st * KT + j] != q_rid) x[j] += kMaskLog2;
         }
         if (k0 + KT > Nk) {  // after the add: K rows past Nk are stale shared memory, S there may be anything
 #pragma unroll
@@ -405,8 +454,8 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
         if (lane == 0) mbar_arrive(&p_full[wg]);
       }
       // ---- epilogue: O_g final
-      mbar_wait(&bar_s[wg], s_cnt & 1);
-      ++s_cnt;
+      mbar_wait2(&o_full[wg], o_cnt & 1);
+      ++o_cnt;
       tcgen05_fence_after();
       {
         uint32_t v[32];
@@ -501,12 +550,12 @@ template <int NWG, int KW, int VAR>
 int launch2_var(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnTcArgs& a, A2Geom tg,
                 cudaStream_t st) {
   auto kern = attn2_kernel<NWG, KW, VAR>;
-  static bool configured[16] = {false};
+  static bool configured[kMaxDevices] = {false};
   int dev = 0;
   GRL_CUDA(cudaGetDevice(&dev));
-  if (dev < 0 || dev >= 16 || !configured[dev]) {
+  if (dev < 0 || dev >= kMaxDevices || !configured[dev]) {
     GRL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, A2Smem<NWG>::TOTAL));
-    if (dev >= 0 && dev < 16) configured[dev] = true;
+    if (dev >= 0 && dev < kMaxDevices) configured[dev] = true;
   }
   const int Nq = a.gq.wh * a.gq.ww;
   tg.n_qg = ceil_div(Nq, NWG * kQT);

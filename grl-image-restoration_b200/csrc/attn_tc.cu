@@ -414,10 +414,13 @@ __global__ void __launch_bounds__(kAttnThreads, (KT <= 32 ? 4 : KT <= 64 ? 3 : 2
 template <int KT, int KW, int VAR>
 static int launch_attn_var(const AttnTcArgs& a, unsigned nblk, cudaStream_t st) {
   auto kern = attn_tc_kernel<KT, KW, VAR>;
-  static bool configured = false;
-  if (!configured) {
+  // the attribute is per device: a process that drives several GPUs configures each one once
+  static bool configured[kMaxDevices] = {false};
+  int dev = 0;
+  GRL_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= kMaxDevices || !configured[dev]) {
     GRL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnSmem<KT>::TOTAL));
-    configured = true;
+    if (dev >= 0 && dev < kMaxDevices) configured[dev] = true;
   }
   kern<<<nblk, kAttnThreads, AttnSmem<KT>::TOTAL, st>>>(a);
   GRL_LAUNCH_CHECK("attn_tc_kernel");

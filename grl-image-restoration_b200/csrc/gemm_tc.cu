@@ -472,10 +472,13 @@ static int make_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t
 template <int BN, int EPI, bool CONV>
 static int launch_one(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmTcArgs& a, dim3 grid, cudaStream_t st) {
   auto kern = gemm_tc_kernel<BN, EPI, CONV>;
-  static bool configured = false;
-  if (!configured) {
+  // the attribute is per device: a process that drives several GPUs configures each one once
+  static bool configured[kMaxDevices] = {false};
+  int dev = 0;
+  GRL_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= kMaxDevices || !configured[dev]) {
     GRL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<BN>::TOTAL));
-    configured = true;
+    if (dev >= 0 && dev < kMaxDevices) configured[dev] = true;
   }
   kern<<<grid, 192, GemmSmem<BN>::TOTAL, st>>>(tmA, tmB, a);
   GRL_LAUNCH_CHECK("gemm_tc_kernel");

@@ -41,6 +41,8 @@ inline int fail(int code, const char* fmt, ...) {
       return ::grl::fail(GRL_ERR_CUDA, "launch of %s failed: %s", name, cudaGetErrorString(e__));      \
   } while (0)
 
+constexpr int kMaxDevices = 64;  // per-device one-time kernel attributes (cudaFuncSetAttribute is per device)
+
 inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 __device__ __forceinline__ float warp_sum(float v) {

@@ -561,6 +561,10 @@ class GRL(nn.Module):
         self.anchor_window_down_factor = anchor_window_down_factor
         if out_proj_type != "linear":
             raise NotImplementedError("only out_proj_type='linear' is on the B200 hot path")
+        if any(int(v) != 0 for v in list(pretrained_window_size) + list(pretrained_stripe_size)):
+            # ops.get_relative_coords_table_all divides by the pretrained size when it is > 0 (ops.py:225-271); no released
+            # config sets it, and the closed-form tables here always normalise by the current size
+            raise NotImplementedError("pretrained_window_size / pretrained_stripe_size != 0 are not on the B200 hot path")
 
         self.conv_first = nn.Conv2d(in_channels, embed_dim, 3, 1, 1)
         self.norm_start = norm_layer(embed_dim)
@@ -635,7 +639,8 @@ class GRL(nn.Module):
             raise ValueError(f"precision must be fp32 / fp16 / bf16 / auto, got {precision!r}")
         ok = all(tc.supported(self.embed_dim, b.num_heads_w, b.num_heads_s) for l in self.layers for b in l.blocks)
         if precision in ("fp16", "bf16") and not ok:
-            raise RuntimeError("this architecture is outside the tensor-core path (head_dim > 32 or C % 4 != 0)")
+            raise RuntimeError(f"this architecture is outside the tensor-core path (needs head_dim <= 32, <= 8 heads, C % 4 == 0 "
+                               f"and C <= {tc.LN_MAX_C}); use precision='fp32' or 'auto'")
         self.precision = ("fp16" if precision == "auto" else precision) if (precision != "fp32" and ok) else "fp32"
         for l in self.layers:
             for b in l.blocks:

@@ -30,10 +30,16 @@ def round_up(a, b):
     return (a + b - 1) // b * b
 
 
+LN_MAX_C = 188  # the LayerNorm epilogue keeps a whole 128 x C fp32 row tile in the GEMM's staging area (gemm_tc.cu)
+
+
 def supported(C, heads_w, heads_s):
+    """Architectures the tensor-core path covers: head_dim <= 32 (one 32-wide slot per head), <= 8 heads per
+    attention, C % 4 == 0 and C <= LN_MAX_C (launch_gemm_tc's LayerNorm-epilogue limit).  Anything else runs on the
+    fp32 kernels ("auto") or is rejected up front (explicit "fp16" / "bf16")."""
     c = C // 2
-    return (C % 4 == 0 and c % heads_w == 0 and c % heads_s == 0 and c // heads_w <= SLOT and c // heads_s <= SLOT
-            and heads_w <= 8 and heads_s <= 8)
+    return (C % 4 == 0 and C <= LN_MAX_C and c % heads_w == 0 and c % heads_s == 0 and c // heads_w <= SLOT
+            and c // heads_s <= SLOT and heads_w <= 8 and heads_s <= 8)
 
 
 def _h16(*shape, device, fmt, zero=False):

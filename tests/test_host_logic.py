@@ -1,0 +1,79 @@
+"""Host-side logic that needs no GPU: tensor-core eligibility, checkpoint ingestion, constructor guards."""
+import pytest
+import torch
+
+
+class HParams:  # stands in for the omegaconf object Lightning pickles next to the tensors (not a tensor-only pickle)
+    tile = 0
+
+
+def test_tc_supported_limits(pkg):
+    """'auto' must only pick the tensor-core path for architectures its kernels accept: the LayerNorm
+    epilogue of gemm_tc.cu holds a whole 128 x C fp32 row tile, C <= 188."""
+    from grl_image_restoration_b200 import tc
+
+    assert tc.supported(180, 3, 3) and tc.supported(64, 2, 2) and tc.supported(128, 2, 2)
+    assert not tc.supported(192, 3, 3)   # C > LN_MAX_C
+    assert not tc.supported(256, 4, 4)
+    assert not tc.supported(288, 6, 6)
+    assert not tc.supported(180, 2, 2)   # head_dim 45 > 32
+    assert not tc.supported(182, 7, 7)   # C % 4 != 0
+    assert tc.LN_MAX_C == 188
+
+
+def test_auto_precision_falls_back_for_wide_models(pkg):
+    cfg = pkg.configs.micro_config(embed_dim=192, heads=3, window=8, stripe=(8, 16), df=2, img_size=32)
+    m = pkg.GRL(**cfg)
+    assert m.set_precision("auto") == "fp32"
+    with pytest.raises(RuntimeError, match="tensor-core path"):
+        m.set_precision("fp16")
+    cfg = pkg.configs.micro_config(embed_dim=36, heads=2)
+    assert pkg.GRL(**cfg).set_precision("auto") == "fp16"
+
+
+def test_pretrained_sizes_rejected(pkg):
+    cfg = pkg.configs.micro_config()
+    with pytest.raises(NotImplementedError):
+        pkg.GRL(**cfg, pretrained_window_size=[8, 8])
+    with pytest.raises(NotImplementedError):
+        pkg.GRL(**cfg, pretrained_stripe_size=[0, 16])
+
+
+def test_checkpoint_ingestion_variants(pkg, tmp_path):
+    """tools/trainer.py:93-115: Lightning 'state_dict' with engine buffers and model.* prefix, extra engine keys, a
+    'params' wrapper, a bare state dict; files are read with weights_only=False (hyper_parameters are pickled)."""
+    from grl_image_restoration_b200 import checkpoint
+
+    cfg = pkg.configs.micro_config()
+    src = pkg.GRL(**cfg)
+    with torch.no_grad():
+        for p in src.parameters():
+            p.add_(0.01)
+    sd = src.state_dict()
+
+    def fresh():
+        return pkg.GRL(**cfg)
+
+    def same(m):
+        return all(torch.equal(v, sd[k]) for k, v in m.state_dict().items())
+
+    # 1. Lightning checkpoint: model.* keys + engine buffers + other engine state + reference-style buffers
+    pl = {"model." + k: v.clone() for k, v in sd.items()}
+    pl.update(current_val_metric=torch.zeros(1), best_val_metric=torch.zeros(1), best_iter=torch.zeros(1))
+    pl["loss.weight"] = torch.ones(3)
+    pl["model.index_w"] = torch.zeros(4, dtype=torch.int64)
+    pl["model.mask_sh_a2w"] = torch.zeros(4)
+
+    path = str(tmp_path / "last.ckpt")
+    torch.save({"state_dict": pl, "hyper_parameters": HParams(), "epoch": 3}, path)
+    m = fresh()
+    checkpoint.load_reference_checkpoint(m, path)
+    assert same(m)
+    # 2. 'params' wrapper
+    m = fresh()
+    checkpoint.load_reference_checkpoint(m, {"params": {k: v.clone() for k, v in sd.items()}})
+    assert same(m)
+    # 3. bare state dict
+    m = fresh()
+    checkpoint.load_reference_checkpoint(m, {k: v.clone() for k, v in sd.items()})
+    assert same(m)

@@ -1,0 +1,167 @@
+"""Dev tool: the three attention launches of one GRL-Base block (cfg4 geometry) per kernel variant, compared with an fp32
+materialised-attention reference computed on the GPU on the same 16-bit operands: error statistics, run-to-run
+determinism, batch invariance and CUDA-event timings.   python tools/attn_debug.py [--variants 0,5] [--batch 2]"""
+import argparse
+import math
+import os
+import sys
+
+import torch
+import torch.nn.functional as F
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+from _pkgload import load_package  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--variants", default="0,5")
+ap.add_argument("--batch", type=int, default=2)
+ap.add_argument("--size", type=int, default=256)
+ap.add_argument("--heads", type=int, default=3)
+ap.add_argument("--scale", type=float, default=14.0, help="|logit| range of q.k in log2 units")
+ap.add_argument("--iters", type=int, default=5)
+a = ap.parse_args()
+pkg = load_package()
+import grl_oracle as orc  # noqa: E402
+from grl_image_restoration_b200 import capi, geometry as G, tc  # noqa: E402
+
+dev = torch.device("cuda:0")
+B, H, W, heads, d = a.batch, a.size, a.size, a.heads, 30
+L = H * W
+g = torch.Generator().manual_seed(31)
+
+
+def ref_attn(q, k, v, idx, table, mask):
+    """q (Bw,h,Nq,32) k,v (Bw,h,Nk,32) fp32 on GPU; table (h, rows) log2 domain; mask (nW,Nq,Nk) or None."""
+    out = torch.empty(q.shape[0], q.shape[1], q.shape[2], 32, device=dev)
+    nW = mask.shape[0] if mask is not None else 1
+    bias = table[:, idx.reshape(-1)].view(table.shape[0], *idx.shape)
+    for b0 in range(0, q.shape[0], 16):
+        s = q[b0:b0 + 16] @ k[b0:b0 + 16].transpose(-1, -2) + bias.unsqueeze(0)
+        if mask is not None:
+            wi = (torch.arange(b0, min(b0 + 16, q.shape[0]), device=dev) % nW)
+            s = s + (mask[wi] * 1.4426950408889634).unsqueeze(1)
+        p = torch.softmax(s * math.log(2.0), dim=-1)
+        out[b0:b0 + 16] = p @ v[b0:b0 + 16]
+    return out
+
+
+def stats(name, got, ref):
+    e = (got - ref).abs()
+    print(f"  {name}: max-abs {e.max().item():.3e} mean-abs {e.mean().item():.3e} rms {e.pow(2).mean().sqrt().item():.3e} "
+          f"(ref rms {ref.pow(2).mean().sqrt().item():.3e})")
+
+
+def timeit(fn):
+    fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(a.iters):
+        e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    return sorted(ts)[len(ts) // 2]
+
+
+# ------------------------------------------------------------------ operands (what the QKV / anchor epilogues write)
+ws, ss, df = (32, 32), (64, 64), 2
+nsl = 6 * heads
+qkv = torch.zeros(B, L, nsl, 32)
+qkv[..., :d] = torch.randn(B, L, nsl, d, generator=g)
+for half in (0, 1):
+    base = half * 3 * heads
+    qkv[:, :, base:base + 2 * heads, :d] = F.normalize(qkv[:, :, base:base + 2 * heads, :d], dim=-1)
+    qkv[:, :, base:base + heads] *= a.scale
+    qkv[:, :, base + 2 * heads:base + 3 * heads, 31] = 1.0  # ones column
+Ha, Wa = H // df, W // df
+anc = torch.zeros(B, Ha * Wa, heads, 32)
+anc[..., :d] = F.normalize(torch.randn(B, Ha * Wa, heads, d, generator=g), dim=-1)
+q16 = qkv.view(B * L, nsl * 32).to(dev).half()
+a16 = anc.view(B * Ha * Wa, heads * 32).to(dev).half()
+qf, af = q16.float().view(B, H, W, nsl, 32), a16.float().view(B, Ha, Wa, heads, 32)
+tw = (torch.rand(heads, (2 * ws[0] - 1) * (2 * ws[1] - 1), generator=g) * 16 * tc.LOG2E).to(dev)
+ass = [s // df for s in ss]
+rows_s = (ss[0] + ass[0] - 1) * (ss[1] + ass[1] - 1)
+t1 = (torch.rand(heads, rows_s, generator=g) * 16 * tc.LOG2E).to(dev)
+t2 = (torch.rand(heads, rows_s, generator=g) * 16 * tc.LOG2E).to(dev)
+sw, sh = ws[0] // 2, [s // 2 for s in ss]
+ash = [s // df for s in sh]
+
+# ------------------------------------------------------------------ fp32 references on the GPU
+t = torch.roll(qf[:, :, :, :3 * heads].reshape(B, H, W, -1), (-sw, -sw), (1, 2))
+win = orc.partition(t, ws).reshape(-1, ws[0] * ws[1], 3, heads, 32).permute(2, 0, 3, 1, 4)
+mask_w = orc.shift_mask([H, W], list(ws), [sw, sw]).to(dev)
+o = ref_attn(win[0], win[1], win[2], orc.position_index(list(ws)).to(dev), tw, mask_w)
+o = o.transpose(1, 2).reshape(-1, ws[0], ws[1], heads * 32)
+ref_w = torch.roll(orc.unpartition(o, ws, (H, W)), (sw, sw), (1, 2)).reshape(B * L, heads * 32)
+
+t = torch.roll(qf[:, :, :, 3 * heads:].reshape(B, H, W, -1), (-sh[0], -sh[1]), (1, 2))
+ar = torch.roll(af.reshape(B, Ha, Wa, -1), (-ash[0], -ash[1]), (1, 2))
+tws = orc.partition(t, ss).reshape(-1, ss[0] * ss[1], 3, heads, 32).permute(2, 0, 3, 1, 4)
+aw = orc.partition(ar, ass).reshape(-1, ass[0] * ass[1], heads, 32).permute(0, 2, 1, 3)
+ma = orc.shift_mask([H, W], list(ss), sh, df, False).to(dev)
+mw = orc.shift_mask([H, W], list(ss), sh, df, True).to(dev)
+x1_ref = ref_attn(aw, tws[1], tws[2], orc.position_index(list(ss), df, False).to(dev), t1, ma)
+y = ref_attn(tws[0], aw, x1_ref.half().float(), orc.position_index(list(ss), df, True).to(dev), t2, mw)
+y = y.transpose(1, 2).reshape(-1, ss[0], ss[1], heads * 32)
+ref_s = torch.roll(orc.unpartition(y, ss, (H, W)), (sh[0], sh[1]), (1, 2)).reshape(B * L, heads * 32)
+
+gw = G.token_grid((H, W), ws, (sw, sw))
+tok, ag = G.token_grid((H, W), ss, sh), G.anchor_grid((H, W), ss, sh, df)
+nW = (H // ss[0]) * (W // ss[1])
+bw_, b1_, b2_ = tc.shifted_copies(tw), tc.shifted_copies(t1), tc.shifted_copies(t2)
+
+
+def run_all(q16_, a16_, Bn):
+    merged = torch.zeros(Bn * L, 2 * heads * 32, device=dev, dtype=torch.float16)
+    x1d = torch.empty(Bn * nW * heads * ass[0] * ass[1], 32, device=dev, dtype=torch.float16)
+    tc.attention(gw, gw, q16_, 0, q16_, heads * 32, q16_, 2 * heads * 32, merged, 0, Bn, heads, bw_, True, ones_col=True)
+    tc.attention(ag, tok, a16_, 0, q16_, 4 * heads * 32, q16_, 5 * heads * 32, x1d, 0, Bn, heads, b1_, True, o_dense=True, ones_col=True)
+    tc.attention(tok, ag, q16_, 3 * heads * 32, a16_, 0, x1d, 0, merged, heads * 32, Bn, heads, b2_, True, v_dense=True, ones_col=True)
+    return merged, x1d
+
+
+for variant in [int(v) for v in a.variants.split(",")]:
+    capi.lib().grl_tc_attn_variant(variant)
+    print(f"=== variant {variant}  (B={B}, {H}x{W}, heads {heads}, logit scale {a.scale})")
+    m1, x1 = run_all(q16, a16, B)
+    torch.cuda.synchronize()
+    m2, x2 = run_all(q16, a16, B)
+    torch.cuda.synchronize()
+    stats("window  vs fp32", m1[:, :heads * 32].float()[..., :], ref_w)
+    stats("stripe  vs fp32", m1[:, heads * 32:].float(), ref_s)
+    stats("X1      vs fp32", x1.float().view(x1_ref.shape), x1_ref)
+    if variant >= 5:  # where are the bad rows?  (window launch: item = ((h * nBW + bw) * n_qg + qg), NWG = 3)
+        e = (m1[:, :heads * 32].float() - ref_w).abs().view(B, H, W, heads, 32).amax(-1)  # (B, H, W, heads)
+        t_ = torch.roll(e, (-sw, -sw), (1, 2))
+        ew = orc.partition(t_, ws).reshape(B, -1, ws[0] * ws[1], heads)  # (B, nW, Nq, heads)
+        nWw = ew.shape[1]
+        et = ew.view(B, nWw, 8, 128, heads).amax(3)  # per q tile
+        bad = (et > 0.02).nonzero().tolist()
+        print(f"  bad (b, window, qtile, head) combos: {len(bad)} of {et.numel()}")
+        nqg, nBW = 3, B * nWw
+        for b_, w_, qt_, h_ in bad[:40]:
+            item = (h_ * nBW + (b_ * nWw + w_)) * nqg + qt_ // 3
+            rows_bad = (ew[b_, w_, qt_ * 128:(qt_ + 1) * 128, h_] > 0.02).sum().item()
+            print(f"    b {b_} win {w_} (wr {w_ // 8}, wc {w_ % 8}) qtile {qt_} (wg {qt_ % 3}) head {h_}: item {item} cta {item % 148} seq {item // 148} "
+                  f"bad rows {rows_bad}/128 max {et[b_, w_, qt_, h_].item():.3f}")
+    print(f"  run-to-run identical: merged {torch.equal(m1, m2)}  x1 {torch.equal(x1, x2)}  "
+          f"(max diff {(m1.float() - m2.float()).abs().max().item():.3e})")
+    if B > 1:
+        mb, xb = run_all(q16[:L], a16[:Ha * Wa], 1)
+        torch.cuda.synchronize()
+        print(f"  batch invariant (B=1 vs first image of B={B}): {torch.equal(mb, m1[:L])}  "
+              f"(max diff {(mb.float() - m1[:L].float()).abs().max().item():.3e})")
+    merged = torch.zeros(B * L, 2 * heads * 32, device=dev, dtype=torch.float16)
+    x1d = torch.empty(B * nW * heads * ass[0] * ass[1], 32, device=dev, dtype=torch.float16)
+    tw_ms = timeit(lambda: tc.attention(gw, gw, q16, 0, q16, heads * 32, q16, 2 * heads * 32, merged, 0, B, heads, bw_, True, ones_col=True))
+    t1_ms = timeit(lambda: tc.attention(ag, tok, a16, 0, q16, 4 * heads * 32, q16, 5 * heads * 32, x1d, 0, B, heads, b1_, True, o_dense=True, ones_col=True))
+    t2_ms = timeit(lambda: tc.attention(tok, ag, q16, 3 * heads * 32, a16, 0, x1d, 0, merged, heads * 32, B, heads, b2_, True, v_dense=True, ones_col=True))
+    # score elements per launch: B * L * Nk * heads (window Nk=1024; pass 1: queries = anchors (L/4), Nk = 4096; pass 2: Nk = 1024)
+    el = B * L * 1024 * heads
+    print(f"  window {tw_ms:.3f} ms  stripe pass1 {t1_ms:.3f} ms  pass2 {t2_ms:.3f} ms   "
+          f"({el / tw_ms / 1e6:.0f} / {el / t1_ms / 1e6:.0f} / {el / t2_ms / 1e6:.0f} G score elems/s; MUFU peak at 1.9 GHz = 4500)")
