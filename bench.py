@@ -373,7 +373,7 @@ def main():
         xd = x_host.to(dev, non_blocking=True)
         gd = gt_host.to(dev, non_blocking=True)
         out = forward(xd)
-        p = metrics.psnr(out, gd, border=scale if scale > 1 else 0)
+        p, _ = metrics.psnr_fused(out, gd, border=scale if scale > 1 else 0)  # one fused kernel (csrc/metric.cu)
         if frame:
             return p.cpu(), idx.cpu()
         gv, gi = sharding.gather_metric(p, idx)
@@ -434,7 +434,7 @@ def main():
            "output_mpix_per_s": value * scale * scale, "clocks": clocks, "gpu_launches": int(launches),
            "e2e": {"value": e2e_value, "unit": "Mpix/s", "h2d_bytes_per_step": int(x_host.numel() * 4 + gt_host.numel() * 4),
                    "d2h_bytes_per_step": int(pv.numel() * 4 + pi.numel() * 8),
-                   "includes": "H2D inputs+GT from pinned memory, forward, reference PSNR on device, all-gather, D2H"},
+                   "includes": "H2D inputs+GT from pinned memory, forward, fused PSNR kernel (RGB + luma) on device, all-gather, D2H"},
            "mean_psnr_vs_random_gt_db": mean_psnr, "roofline": roof}
 
     if world == 1 and not a.no_extras:

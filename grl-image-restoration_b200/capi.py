@@ -64,6 +64,7 @@ _SIGNATURES = {
     "grl_tc_gemm": (c_int, [ctypes.POINTER(GrlTcGemm), c_vp]),
     "grl_tc_attn": (c_int, [ctypes.POINTER(GrlTcAttn), c_vp]),
     "grl_tc_attn_variant": (c_int, [c_int]),
+    "grl_psnr_f32": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_sz, c_vp, c_vp, c_vp]),
     "grl_affine_f32": (c_int, [c_vp, c_i64, c_int, c_int, c_int, c_vp, c_vp, c_int, c_vp, c_vp, c_int, c_vp]),
     "grl_linear_f32": (c_int, [c_vp, c_i64, c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_i64, c_int, c_int, c_int, c_f32, c_vp]),
     "grl_conv3x3_f32": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_f32, c_vp]),

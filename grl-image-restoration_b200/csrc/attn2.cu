@@ -17,10 +17,14 @@
 // tcgen05.mma issuer.  (No setmaxnreg: the register pool of a CTA is what its own warps release, and 576 threads at 112
 // registers already use the whole file.)
 //
-// TMEM columns per warpgroup g: [96 g, 96 g + 64) = S_g (fp32) aliased by P_g (16-bit pairs in columns [0, 32));
-// [96 g + 64, 96 g + 96) = O_g.  The tensor pipe executes one thread's MMAs in issue order, so
-//   P V_g(t) ; Q K^T_g(t+1)   issued back to back is hazard free (the second overwrites what the first reads).
+// TMEM columns per warpgroup g (base 160 g): [0, 64) = S buffer 0, [64, 128) = S buffer 1, [128, 160) = O_g.  S_g(t) lands
+// in buffer t & 1 and is overwritten in place by P_g(t) (16-bit pairs in the first 32 columns of the buffer).  Q K^T runs
+// TWO tiles ahead of the softmax: the issuer sends  P V_g(t) ; Q K^T_g(t+2)  back to back -- both touch buffer t & 1, and
+// the tensor pipe executes one thread's MMAs in issue order, so the second overwrites what the first has read -- which
+// means S_g(t+1) is already complete when the softmax warps finish tile t: they never wait for the MMA round trip.
 #include <stdlib.h>
+
+#include <algorithm>
 
 #include "attn_tc.cuh"
 #include "grl_common.cuh"
@@ -33,10 +37,38 @@ namespace tc {
 
 namespace {
 
+// ---- differential-timing builds (tools/attn2_diag.py): each GRL_A2_DIAG_* define removes ONE ingredient so that its cost
+// shows up as a time difference.  Results of such builds are WRONG by construction; the default build defines none.
+#ifdef GRL_A2_DIAG_NOBIAS
+#define A2_BIAS(expr) make_float4(0.f, 0.f, 0.f, 0.f)
+#else
+#define A2_BIAS(expr) (expr)
+#endif
+#ifdef GRL_A2_DIAG_NOEXP
+#define A2_EX2(x) (x)
+#else
+#define A2_EX2(x) ex2(x)
+#endif
+#ifdef GRL_A2_DIAG_NOLDTM
+#define A2_LDTM(stmt)
+#else
+#define A2_LDTM(stmt) stmt
+#endif
+#ifdef GRL_A2_DIAG_NOSTTM
+#define A2_STTM(stmt)
+#else
+#define A2_STTM(stmt) stmt
+#endif
+#ifdef GRL_A2_DIAG_NOMAX
+#define A2_MAX(expr) 0.f
+#else
+#define A2_MAX(expr) (expr)
+#endif
+
 constexpr int kKT2 = 64;       // keys per tile
-constexpr int kStages2 = 4;    // K / V ring depth
+constexpr int kStages2 = 5;    // K / V ring depth (tiles t .. t+2 are live in the MMA pipeline, the rest is prefetch)
 constexpr float kTau = 8.0f;   // lazy-rescale threshold (log2 units): P <= 2^8 stays far inside fp16 / bf16 range
-constexpr int kColsPerWg = 96;
+constexpr int kColsPerWg = 160;  // TMEM columns per warpgroup: S buffer 0 | S buffer 1 | O
 
 template <int NWG>
 struct A2Smem {
@@ -46,13 +78,14 @@ struct A2Smem {
   static constexpr int OFF_V = OFF_K + kStages2 * KV_BYTES;
   static constexpr int OFF_META = OFF_V + kStages2 * KV_BYTES;  // int koff[kStages2][KT], krid[kStages2][KT]
   static constexpr int OFF_BAR = OFF_META + kStages2 * 2 * kKT2 * 4;
-  static constexpr int TOTAL = OFF_BAR + 512 + 1024;
+  static constexpr int OFF_BIAS = OFF_BAR + 512;  // optional: the head's 4-copy bias table (16 bytes per table row)
+  static constexpr int TOTAL = OFF_BIAS + 1024;   // + 16 * rows_pad when the table is staged
 };
 
 struct A2Geom {
   int bw_q, bw_k;   // tokens per TMA box
   int n_qg;         // query groups (NWG * 128 rows) per window
-  int n_items;      // heads * B * windows * n_qg
+  int per_head;     // B * windows * n_qg work items per head; CTA b works on head b / (gridDim / heads)
 };
 
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
@@ -102,6 +135,24 @@ __device__ __forceinline__ void mbar_wait2(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// shared-memory loads by 32-bit shared address (the tile base is aligned through integer arithmetic, after which the
+// compiler only sees a generic pointer and would emit generic LD instead of LDS)
+__device__ __forceinline__ float4 lds128(uint32_t saddr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+  return v;
+}
+__device__ __forceinline__ float lds32f(uint32_t saddr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(saddr));
+  return v;
+}
+__device__ __forceinline__ int lds32i(uint32_t saddr) {
+  int v;
+  asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(saddr));
+  return v;
+}
+
 __device__ __forceinline__ float fmax3(float a, float b, float c) {
   float d;
   asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
@@ -112,7 +163,7 @@ struct Item {
   int qg, h, bw, b, wr, wc, nact;
 };
 
-template <int NWG, int KW, int VAR>
+template <int NWG, int KW, int VAR, bool BS>
 __global__ void __launch_bounds__(NWG * 128 + 64, 1)
 attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
              const __grid_constant__ CUtensorMap tmV, const AttnTcArgs a, const A2Geom tg) {
@@ -128,23 +179,24 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::OFF_BAR);
   uint64_t* q_full = bars;                  // [NWG]  Q tile of warpgroup g landed            (TMA tx)
   uint64_t* q_empty = q_full + 4;           // [NWG]  every Q K^T of the item that reads it is done  (tcgen05.commit)
-  uint64_t* bar_s = q_empty + 4;            // [NWG]  S_g(t) ready                               (tcgen05.commit)
-  uint64_t* p_full = bar_s + 4;             // [NWG]  P_g(t) written to TMEM                     (4 warp arrivals)
-  uint64_t* o_full = p_full + 4;            // [NWG]  O_g of the item final (own barrier: bar_s would otherwise complete
-                                            //        twice -- final O, next item's S_0 -- without a p_full in between)
-  uint64_t* kv_full = o_full + 4;           // [kStages2]  K_t, V_t landed                       (TMA tx)
-  uint64_t* kv_empty = kv_full + kStages2;  // [kStages2]  every MMA that reads the stage is done (tcgen05.commit)
-  uint64_t* meta_full = kv_empty + kStages2;  // [kStages2]  koff / rid of the stage written      (32 arrivals)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(meta_full + kStages2);
+  uint64_t* bar_s = q_empty + 4;            // [NWG][2]  S_g(t) ready in buffer t & 1            (tcgen05.commit)
+  uint64_t* p_full = bar_s + 8;             // [NWG]  P_g(t) written to TMEM                     (4 warp arrivals)
+  uint64_t* o_done = p_full + 4;            // [NWG]  P V_g(t) complete, every tile (rescale of O / final O)  (tcgen05.commit)
+  uint64_t* kv_full = o_done + 4;           // [kStages2]  K_t, V_t landed                       (TMA tx)
+  uint64_t* kv_empty = kv_full + 8;         // [kStages2]  every MMA that reads the stage is done (tcgen05.commit)
+  uint64_t* meta_full = kv_empty + 8;       // [kStages2]  koff / rid of the stage written      (32 arrivals)
+  uint64_t* bias_full = meta_full + 8;      // the head's bias table landed in shared memory (BS)   (bulk-copy tx)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bias_full + 1);
+  float* bias_s = reinterpret_cast<float*>(smem + S::OFF_BIAS);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int wg = warp >> 2;
   const int Nq = a.gq.wh * a.gq.ww, Nk = a.gk.wh * a.gk.ww;
   const int nww = a.gq.W / a.gq.ww, nwh = a.gq.H / a.gq.wh;
   const int nW = nwh * nww;
-  const int nBW = a.B * nW;
   const int Wt = a.gq.ww + a.gk.ww - 1;
   const int ntiles = (Nk + KT - 1) / KT;
+  static_assert(NWG * kColsPerWg <= 512, "two S buffers + O per warpgroup: at most 3 warpgroups fit the 512 TMEM columns");
   constexpr uint32_t TMEM_COLS = (NWG * kColsPerWg <= 128) ? 128 : (NWG * kColsPerWg <= 256) ? 256 : 512;
   constexpr int fmt = (VAR & 1) ? FMT_BF16 : FMT_F16;
   constexpr bool ones = (VAR & 2) != 0;
@@ -153,15 +205,17 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
     for (int g = 0; g < NWG; ++g) {
       mbar_init(&q_full[g], 1);
       mbar_init(&q_empty[g], 1);
-      mbar_init(&bar_s[g], 1);
+      mbar_init(&bar_s[2 * g], 1);
+      mbar_init(&bar_s[2 * g + 1], 1);
       mbar_init(&p_full[g], 4);
-      mbar_init(&o_full[g], 1);
+      mbar_init(&o_done[g], 1);
     }
     for (int s = 0; s < kStages2; ++s) {
       mbar_init(&kv_full[s], 1);
       mbar_init(&kv_empty[s], 1);
       mbar_init(&meta_full[s], 32);
     }
+    mbar_init(bias_full, 1);
     mbar_init_fence();
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmK);
@@ -173,12 +227,15 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
   tcgen05_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  auto decode = [&](int item) {
+  // Static head partition: CTA b serves head b / cph only (cph = CTAs per head), so a CTA needs ONE bias table for its
+  // whole life -- it can live in shared memory (BS), and without BS the table stays hot in this SM's L1.
+  const int cph = gridDim.x / a.heads;
+  const int my_h = blockIdx.x / cph, my_c = blockIdx.x - my_h * cph;
+  auto decode = [&](int idx) {
     Item it;
-    it.qg = item % tg.n_qg;
-    item /= tg.n_qg;
-    it.bw = item % nBW;
-    it.h = item / nBW;  // head slowest: CTAs that run concurrently read the same bias table
+    it.qg = idx % tg.n_qg;
+    it.bw = idx / tg.n_qg;
+    it.h = my_h;
     it.b = it.bw / nW;
     const int w = it.bw - it.b * nW;
     it.wr = w / nww;
@@ -209,7 +266,12 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
       uint32_t kv_it = 0, q_cnt[NWG];
 #pragma unroll
       for (int g = 0; g < NWG; ++g) q_cnt[g] = 0;
-      for (int item = blockIdx.x; item < tg.n_items; item += gridDim.x) {
+      if (BS && lane == 0) {  // the head's table: 4 shifted copies, contiguous in global memory, one bulk copy
+        const uint32_t bytes = 16u * (uint32_t)a.rows_pad;
+        mbar_expect_tx(bias_full, bytes);
+        bulk_load_1d(bias_s, a.bias + (size_t)my_h * 4 * a.rows_pad, bytes, bias_full);
+      }
+      for (int item = my_c; item < tg.per_head; item += cph) {
         const Item it = decode(item);
         const bool need_mask = a.use_mask && (it.wr == nwh - 1 || it.wc == nww - 1);
 #pragma unroll
@@ -261,36 +323,39 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
       uint32_t kv_it = 0, q_cnt[NWG], p_cnt[NWG];
 #pragma unroll
       for (int g = 0; g < NWG; ++g) q_cnt[g] = 0, p_cnt[g] = 0;
-      auto issue_qk = [&](int g, int st, bool last) {
+      auto issue_qk = [&](int g, int st, int buf, bool last) {
         const uint32_t q_sa = smem_u32(Qs + g * S::Q_BYTES), k_sa = smem_u32(Ks + st * S::KV_BYTES);
 #pragma unroll
         for (int k = 0; k < kDP / 16; ++k)
-          umma_ss(tmem + g * kColsPerWg, umma_desc(q_sa + k * 32, 16, 512, SWZ_64B), umma_desc(k_sa + k * 32, 16, 512, SWZ_64B),
-                  idesc_qk, k != 0);
+          umma_ss(tmem + g * kColsPerWg + buf * 64, umma_desc(q_sa + k * 32, 16, 512, SWZ_64B),
+                  umma_desc(k_sa + k * 32, 16, 512, SWZ_64B), idesc_qk, k != 0);
         if (last) umma_commit(&q_empty[g]);
+        umma_commit(&bar_s[2 * g + buf]);
       };
-      for (int item = blockIdx.x; item < tg.n_items; item += gridDim.x) {
+      for (int item = my_c; item < tg.per_head; item += cph) {
         const Item it = decode(item);
-        {
-          const int st = kv_it % kStages2;
-          mbar_wait2(&kv_full[st], (kv_it / kStages2) & 1);
+        // prologue: S_g(0) and S_g(1)
+        for (int t0 = 0; t0 < 2 && t0 < ntiles; ++t0) {
+          const int st = (kv_it + t0) % kStages2;
+          mbar_wait2(&kv_full[st], ((kv_it + t0) / kStages2) & 1);
 #pragma unroll
           for (int g = 0; g < NWG; ++g) {
             if (g < it.nact) {
-              mbar_wait2(&q_full[g], q_cnt[g] & 1);
-              ++q_cnt[g];
+              if (t0 == 0) {
+                mbar_wait2(&q_full[g], q_cnt[g] & 1);
+                ++q_cnt[g];
+              }
               if (lane == 0) {
                 tcgen05_fence_after();
-                issue_qk(g, st, ntiles == 1);
-                umma_commit(&bar_s[g]);
+                issue_qk(g, st, t0, t0 + 1 == ntiles);
               }
               __syncwarp();
             }
           }
         }
         for (int t = 0; t < ntiles; ++t, ++kv_it) {
-          const int st = kv_it % kStages2, st1 = (kv_it + 1) % kStages2;
-          if (t + 1 < ntiles) mbar_wait2(&kv_full[st1], ((kv_it + 1) / kStages2) & 1);
+          const int st = kv_it % kStages2, st2 = (kv_it + 2) % kStages2;
+          if (t + 2 < ntiles) mbar_wait2(&kv_full[st2], ((kv_it + 2) / kStages2) & 1);
 #pragma unroll
           for (int g = 0; g < NWG; ++g) {
             if (g < it.nact) {
@@ -299,16 +364,13 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
               if (lane == 0) {
                 tcgen05_fence_after();
                 const uint32_t v_sa = smem_u32(Vs + st * S::KV_BYTES);
-                const uint32_t p_ta = tmem + g * kColsPerWg;
+                const uint32_t wg_ta = tmem + g * kColsPerWg;
+                const uint32_t p_ta = wg_ta + (t & 1) * 64;
 #pragma unroll
                 for (int k = 0; k < KT / 16; ++k)
-                  umma_ts(p_ta + 64, p_ta + k * 8, umma_desc(v_sa + k * 1024, 16, 512, SWZ_64B), idesc_pv, (t | k) != 0);
-                if (t + 1 < ntiles) {
-                  issue_qk(g, st1, t + 2 == ntiles);
-                  umma_commit(&bar_s[g]);
-                } else {
-                  umma_commit(&o_full[g]);
-                }
+                  umma_ts(wg_ta + 128, p_ta + k * 8, umma_desc(v_sa + k * 1024, 16, 512, SWZ_64B), idesc_pv, (t | k) != 0);
+                umma_commit(&o_done[g]);
+                if (t + 2 < ntiles) issue_qk(g, st2, t & 1, t + 3 == ntiles);
               }
               __syncwarp();
             }
@@ -326,10 +388,12 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
   } else {
     // =============================================================== softmax warpgroups: thread = query row
     const int row = tid & 127;
-    const uint32_t ts = tmem + ((uint32_t)((warp & 3) * 32) << 16) + wg * kColsPerWg;  // S / P columns of this row
-    const uint32_t to = ts + 64;                                                         // O columns
-    uint32_t s_cnt = 0, o_cnt = 0, kv_it = 0;
-    for (int item = blockIdx.x; item < tg.n_items; item += gridDim.x) {
+    const uint32_t ts0 = tmem + ((uint32_t)((warp & 3) * 32) << 16) + wg * kColsPerWg;  // S / P buffer 0 of this row
+    const uint32_t to = ts0 + 128;                                                        // O columns
+    bool bias_ready = false;
+    const uint32_t bias_sa = smem_u32(bias_s), koff_sa = smem_u32(koff_s), krid_sa = smem_u32(krid_s);
+    uint32_t s_cnt[2] = {0, 0}, o_cnt = 0, kv_it = 0;  // completions consumed: bar_s[buf], o_done (one per tile)
+    for (int item = my_c; item < tg.per_head; item += cph) {
       const Item it = decode(item);
       if (wg >= it.nact) {
         kv_it += ntiles;
@@ -339,6 +403,10 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
       const bool q_ok = qi < Nq;
       const Tok tq = locate(a.gq, it.wr, it.wc, q_ok ? qi : it.qg * NWG * kQT);
       const float* bias_h = a.bias + (size_t)it.h * 4 * a.rows_pad;
+      if (BS && !bias_ready) {
+        mbar_wait2(bias_full, 0);
+        bias_ready = true;
+      }
       const int base_i = (tq.ih + a.gk.wh - 1) * Wt + tq.iw + a.gk.ww - 1;
       const int q_rid = region_id(a.gq, tq.r, tq.c);
       // shift mask (ops.py:112-157): only windows of the last row / column carry one.  Region id of key (kh, kw) of this
@@ -352,7 +420,8 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
       float m_ref = 0.f, l_run = 0.f;
 
       for (int t = 0; t < ntiles; ++t, ++kv_it) {
-        const int k0 = t * KT, st = kv_it % kStages2;
+        const int k0 = t * KT, st = kv_it % kStages2, buf = t & 1;
+        const uint32_t ts = ts0 + buf * 64;
         const bool full_tile = (KW > 0) && (k0 + KT <= Nk);
         // ---- x = bias (+ mask) - m_ref first: these loads and adds do not depend on S and run while Q K^T is in flight.
         // Nothing here may touch the per-stage metadata: a warpgroup that sat out the previous item is a whole item
@@ -368,6 +437,7 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
             const int s0 = base_i - (kh * Wt + kw0) - 3;  // table index of key kj + 3
             const int cpy = (-s0) & 3;
             const float4* bp = reinterpret_cast<const float4*>(bias_h + (size_t)cpy * a.rows_pad + (s0 + cpy));
+            const uint32_t bps = bias_sa + (uint32_t)(cpy * a.rows_pad + (s0 + cpy)) * 4u;  // BS: LDS.128
             float off_lo = m_ref, off_hi = m_ref;
             if (need_mask && mask_fast) {
               const int rid_lo = 3 * ((int)a1 + (int)(kh >= kh_th)) + (int)b1;
@@ -376,7 +446,7 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
             }
 #pragma unroll
             for (int qd = 0; qd < RW / 4; ++qd) {
-              const float4 bb = __ldg(bp - qd);
+              const float4 bb = A2_BIAS(BS ? lds128(bps - 16u * qd) : __ldg(bp - qd));
               const int j = r0 + 4 * qd;
               const float off = (kw0 + 4 * qd >= kw_th) ? off_hi : off_lo;
               x[j + 0] = bb.w - off, x[j + 1] = bb.z - off, x[j + 2] = bb.y - off, x[j + 3] = bb.x - off;
@@ -384,27 +454,29 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
           }
         }
         // ---- S_t
-        mbar_wait2(&bar_s[wg], s_cnt & 1);
-        ++s_cnt;
+        mbar_wait2(&bar_s[2 * wg + buf], s_cnt[buf] & 1);
+        ++s_cnt[buf];
         tcgen05_fence_after();
         const bool meta_mask = need_mask && !(full_tile && mask_fast);
         if (!full_tile || meta_mask) mbar_wait2(&meta_full[st], (kv_it / kStages2) & 1);  // S_t ready => this fill is the current one
         if (!full_tile) {
 #pragma unroll
-          for (int j = 0; j < KT; ++j) x[j] = __ldg(bias_h + base_i - koff_s[st * KT + j]) - m_ref;
+          for (int j = 0; j < KT; ++j) x[j] = (BS ? lds32f(bias_sa + 4u * (uint32_t)(base_i - lds32i(koff_sa + 4u * (st * KT + j))))
+                       : __ldg(bias_h + base_i - lds32i(koff_sa + 4u * (st * KT + j)))) - m_ref;
         }
 #pragma unroll
         for (int c0 = 0; c0 < KT; c0 += 32) {
-          uint32_t v[32];
-          tmem_ld32(ts + c0, v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 32; ++j) x[c0 + j] += __uint_as_float(v[j]);
+          A2_LDTM({
+            uint32_t v[32];
+            tmem_ld32(ts + c0, v);
+            tmem_ld_wait();
+            _Pragma("unroll") for (int j = 0; j < 32; ++j) x[c0 + j] += __uint_as_float(v[j]);
+          })
         }
         if (meta_mask) {
 #pragma unroll
           for (int j = 0; j < KT; ++j)
-            if (krid_s[st * KT + j] != q_rid) x[j] += kMaskLog2;
+            if (lds32i(krid_sa + 4u * (st * KT + j)) != q_rid) x[j] += kMaskLog2;
         }
         if (k0 + KT > Nk) {  // after the add: K rows past Nk are stale shared memory, S there may be anything
 #pragma unroll
@@ -417,16 +489,22 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
           mx0 = fmax3(mx0, x[j], x[j + 1]);
           mx1 = fmax3(mx1, x[j + 2], x[j + 3]);
         }
-        const float mx = fmax3(mx0, mx1, fmaxf(x[KT - 2], x[KT - 1]));
+        const float mx = A2_MAX(fmax3(mx0, mx1, fmaxf(x[KT - 2], x[KT - 1])));
         // ---- lazy rescale: move the reference only when a row outgrew it by 2^kTau (always on the first tile)
         const bool first = (t == 0);
+        // P V_g(t-1) complete (o_done completes once per tile; consuming EVERY completion, in order, keeps the parity waits
+        // exact -- a parity wait cannot tell phases two apart).  It was issued a whole S-load + max ago: normally no wait.
+        if (!first) {
+          mbar_wait2(&o_done[wg], (o_cnt + t - 1) & 1);
+          tcgen05_fence_after();
+        }
         if (__any_sync(0xffffffffu, first || mx > kTau)) {
           float delta = first ? mx : fmaxf(mx, 0.f);
           if (!(fabsf(delta) < 1e30f)) delta = 0.f;  // rows of a partial query tile hold garbage
           m_ref += delta;
 #pragma unroll
           for (int j = 0; j < KT; ++j) x[j] -= delta;
-          if (!first) {  // O_g holds P V of tiles < t (complete: bar_s(t) covers every earlier MMA of the issuer)
+          if (!first) {  // O_g holds P V of tiles < t (P V(t-1) complete: waited for above)
             const float sc = ex2(-delta);
             uint32_t v[32];
             tmem_ld32(to, v);
@@ -442,20 +520,20 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
         float ps0 = 0.f, ps1 = 0.f;
 #pragma unroll
         for (int c = 0; c < KT / 2; ++c) {
-          const float p0 = ex2(x[2 * c]), p1 = ex2(x[2 * c + 1]);
+          const float p0 = A2_EX2(x[2 * c]), p1 = A2_EX2(x[2 * c + 1]);
           if (!ones) ps0 += p0, ps1 += p1;
           pk[c] = (fmt == FMT_BF16) ? pack_bf16(p0, p1) : pack_f16(p0, p1);
         }
         if (!ones) l_run += ps0 + ps1;
-        tmem_st32(ts, pk);
+        A2_STTM(tmem_st32(ts, pk));
         tmem_st_wait();
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_full[wg]);
       }
       // ---- epilogue: O_g final
-      mbar_wait2(&o_full[wg], o_cnt & 1);
-      ++o_cnt;
+      mbar_wait2(&o_done[wg], (o_cnt + ntiles - 1) & 1);
+      o_cnt += ntiles;
       tcgen05_fence_after();
       {
         uint32_t v[32];
@@ -546,36 +624,50 @@ int sm_count() {
   return n[dev];
 }
 
-template <int NWG, int KW, int VAR>
+constexpr int kMaxSmem = 232448;  // 227 KB: the per-CTA shared-memory limit of sm_100
+
+template <int NWG, int KW, int VAR, bool BS>
 int launch2_var(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnTcArgs& a, A2Geom tg,
                 cudaStream_t st) {
-  auto kern = attn2_kernel<NWG, KW, VAR>;
+  auto kern = attn2_kernel<NWG, KW, VAR, BS>;
   static bool configured[kMaxDevices] = {false};
   int dev = 0;
   GRL_CUDA(cudaGetDevice(&dev));
   if (dev < 0 || dev >= kMaxDevices || !configured[dev]) {
-    GRL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, A2Smem<NWG>::TOTAL));
+    GRL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, BS ? kMaxSmem : A2Smem<NWG>::TOTAL));
     if (dev >= 0 && dev < kMaxDevices) configured[dev] = true;
   }
   const int Nq = a.gq.wh * a.gq.ww;
   tg.n_qg = ceil_div(Nq, NWG * kQT);
-  const long long items = (long long)a.heads * a.B * (a.gq.H / a.gq.wh) * (a.gq.W / a.gq.ww) * tg.n_qg;
-  GRL_REQUIRE(items < (1ll << 31), "attn2: too many work items");
-  tg.n_items = (int)items;
-  const unsigned grid = (unsigned)min((long long)sm_count(), items);
-  kern<<<grid, NWG * 128 + 64, A2Smem<NWG>::TOTAL, st>>>(tq, tk, tv, a, tg);
+  const long long per_head = (long long)a.B * (a.gq.H / a.gq.wh) * (a.gq.W / a.gq.ww) * tg.n_qg;
+  GRL_REQUIRE(per_head * a.heads < (1ll << 31), "attn2: too many work items");
+  tg.per_head = (int)per_head;
+  const long long cph = std::max(1ll, std::min((long long)(sm_count() / a.heads), per_head));  // CTAs per head
+  const unsigned grid = (unsigned)(cph * a.heads);
+  const int smem = A2Smem<NWG>::TOTAL + (BS ? 16 * a.rows_pad : 0);
+  kern<<<grid, NWG * 128 + 64, smem, st>>>(tq, tk, tv, a, tg);
   GRL_LAUNCH_CHECK("attn2_kernel");
   return GRL_OK;
+}
+
+template <int NWG, int KW, int VAR>
+int launch2_bs(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnTcArgs& a, const A2Geom& tg,
+               cudaStream_t st) {
+  // the 4-copy table in shared memory when it fits next to the tiles: LDS.128 costs 4 wavefronts where the L1 path pays
+  // ~7.5 tag lookups (the 128-byte runs of the four copies are not line aligned) -- the L1 data pipe was the busiest unit
+  static const bool off = [] { const char* e = getenv("GRL_ATTN2_NO_SMEM_BIAS"); return e && e[0] == '1'; }();
+  if (KW > 0 && !off && A2Smem<NWG>::TOTAL + 16 * a.rows_pad <= kMaxSmem) return launch2_var<NWG, KW, VAR, (KW > 0)>(tq, tk, tv, a, tg, st);
+  return launch2_var<NWG, KW, VAR, false>(tq, tk, tv, a, tg, st);
 }
 
 template <int NWG, int KW>
 int launch2_kw(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnTcArgs& a, const A2Geom& tg,
                cudaStream_t st) {
   switch ((a.fmt == FMT_BF16 ? 1 : 0) | (a.ones_col ? 2 : 0)) {
-    case 0: return launch2_var<NWG, KW, 0>(tq, tk, tv, a, tg, st);
-    case 1: return launch2_var<NWG, KW, 1>(tq, tk, tv, a, tg, st);
-    case 2: return launch2_var<NWG, KW, 2>(tq, tk, tv, a, tg, st);
-    default: return launch2_var<NWG, KW, 3>(tq, tk, tv, a, tg, st);
+    case 0: return launch2_bs<NWG, KW, 0>(tq, tk, tv, a, tg, st);
+    case 1: return launch2_bs<NWG, KW, 1>(tq, tk, tv, a, tg, st);
+    case 2: return launch2_bs<NWG, KW, 2>(tq, tk, tv, a, tg, st);
+    default: return launch2_bs<NWG, KW, 3>(tq, tk, tv, a, tg, st);
   }
 }
 
@@ -599,7 +691,7 @@ int launch_attn2(const AttnTcArgs& a, cudaStream_t st) {
   A2Geom tg;
   tg.bw_q = box_tokens2(a.gq);
   tg.bw_k = box_tokens2(a.gk);
-  tg.n_qg = tg.n_items = 0;
+  tg.n_qg = tg.per_head = 0;
   if (tg.bw_q == 0 || tg.bw_k == 0) return 1;
   if (a.gq.W < tg.bw_q || a.gk.W < tg.bw_k) return 1;
   if ((reinterpret_cast<uintptr_t>(a.q) | reinterpret_cast<uintptr_t>(a.k) | reinterpret_cast<uintptr_t>(a.v)) & 15) return 1;

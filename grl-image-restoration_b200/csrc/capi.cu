@@ -309,4 +309,13 @@ int grl_tc_attn(const GrlTcAttn* p, void* stream) {
 
 int grl_tc_attn_variant(int variant) { return tc::attn_variant(variant); }
 
+int grl_psnr_f32(const float* restored, const float* target, int B, int C, int H, int W, int border, void* workspace,
+                 size_t workspace_bytes, float* psnr_rgb, float* psnr_y, void* stream) {
+  GRL_REQUIRE(restored && target && psnr_rgb, "psnr: null argument");
+  GRL_REQUIRE(workspace && workspace_bytes >= sizeof(unsigned long long) * 2 * (size_t)(B > 0 ? B : 0),
+              "psnr: workspace %zu bytes < %zu", workspace_bytes, sizeof(unsigned long long) * 2 * (size_t)(B > 0 ? B : 0));
+  return launch_psnr(restored, target, B, C, H, W, border, (unsigned long long*)workspace, psnr_rgb, psnr_y,
+                     (cudaStream_t)stream);
+}
+
 }  // extern "C"

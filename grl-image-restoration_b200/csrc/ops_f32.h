@@ -62,5 +62,8 @@ int launch_channel_gate_from_partial(const float* partial, int chunks, int B, lo
                                      cudaStream_t st);
 int check_grid(const GrlGrid& g, const char* what);
 int launch_attn(const AttnArgs& a, cudaStream_t st);
+// fused tensor_round + shave + squared-error reduction (RGB and luma) -> per-image PSNR (metric.cu)
+int launch_psnr(const float* restored, const float* target, int B, int C, int H, int W, int border,
+                unsigned long long* workspace, float* psnr_rgb, float* psnr_y, cudaStream_t st);
 
 }  // namespace grl

@@ -3,7 +3,9 @@
 Reference: engines/base.py:255-268 (round -> shave for SR -> metrics), utils/utils_image.py:8-11 (shave), :30-33
 (tensor_round), :43-80 (rgb2ycbcr, MATLAB coefficients, rounded to 8 bit), utils/metrics/psnr.py:44-48 (psnr),
 utils/metrics/ssim.py:17-82 (Gaussian-window SSIM, 11 taps, sigma 1.5, taps rounded to 6 decimals, zero padding).
-Plain torch ops: this is the caller side of the hot path, not a kernel.
+psnr_fused() is the hand-written kernel (csrc/metric.cu, grl_psnr_f32) the benchmarked validation step uses for PSNR
+(RGB and luma); the torch-op functions below define the same quantities on any device (SSIM stays torch ops) and are
+what the CPU tests pin against the reference's own functions.
 """
 import math
 
@@ -35,6 +37,25 @@ def psnr(restored, target, border=0, channel="rgb"):
     if channel == "y":
         a, b = rgb_to_y(a), rgb_to_y(b)
     return -10 * (a - b).pow(2).mean([-3, -2, -1]).log10()
+
+
+def psnr_fused(restored, target, border=0):
+    """(psnr_rgb, psnr_y), each (B,), from ONE fused kernel over CUDA fp32 (B, C, H, W) images: tensor_round + shave +
+    exact integer squared-error reduction (csrc/metric.cu).  No torch math on the images."""
+    from . import capi
+
+    capi.require_device(restored)
+    capi.require_device(target)
+    if restored.shape != target.shape or restored.dim() != 4:
+        raise RuntimeError(f"grl_b200: psnr_fused needs two (B, C, H, W) tensors of one shape, got {tuple(restored.shape)} / {tuple(target.shape)}")
+    a = restored if (restored.dtype == torch.float32 and restored.is_contiguous()) else restored.float().contiguous()
+    b = target if (target.dtype == torch.float32 and target.is_contiguous()) else target.float().contiguous()
+    B, C, H, W = a.shape
+    ws = torch.empty(2 * max(B, 1), device=a.device, dtype=torch.int64)
+    out = torch.empty(2, B, device=a.device, dtype=torch.float32)
+    capi.check(capi.lib().grl_psnr_f32(capi.ptr(a), capi.ptr(b), B, C, H, W, int(border), capi.ptr(ws), ws.numel() * 8,
+                                       capi.ptr(out[0]), capi.ptr(out[1]), capi.stream()))
+    return out[0], out[1]
 
 
 def _gaussian_window(channels, size, sigma, like):

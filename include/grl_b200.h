@@ -233,6 +233,16 @@ int grl_tc_attn(const GrlTcAttn* p, void* stream);
  * (unset = 0).  Returns the previous value; a value outside {0..4} only queries.  Same results contract as variant 0. */
 int grl_tc_attn_variant(int variant);
 
+/* ---- validation metric -------------------------------------------------- */
+/* Per-image PSNR of the reference's validation step in one fused pass: tensor_round (utils/utils_image.py:30-33) of
+ * both images, `border` pixels shaved on every side (engines/base.py:265-267, utils_image.py:8-11), mean squared error
+ * over (C, H, W) and -10 log10 (utils/metrics/psnr.py:44-48).  restored / target: (B, C, H, W) fp32, C <= 4.
+ * psnr_y (may be NULL): the same on the luma of MATLAB's rgb2ycbcr rounded to 8 bit (utils_image.py:43-80) when C == 3,
+ * else a copy of psnr_rgb.  The error is accumulated exactly (integers), so the result does not depend on the launch
+ * geometry.  workspace: 16 * B bytes of device memory (zeroed by the call). */
+int grl_psnr_f32(const float* restored, const float* target, int B, int C, int H, int W, int border, void* workspace,
+                 size_t workspace_bytes, float* psnr_rgb, float* psnr_y, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
