@@ -13,8 +13,8 @@
 //   * while one warpgroup waits for its P V / next Q K^T round trip, the other NWG-1 keep the MUFU pipe busy -- the
 //     exp2 unit (16 / clk / SM) is the binding resource at head_dim 32, not the tensor pipe.
 //
-// Roles (threads = NWG * 128 + 64): warpgroups 0..NWG-1 softmax; warp 4 NWG = TMA producer, warp 4 NWG + 1 = single-thread
-// tcgen05.mma issuer.  (No setmaxnreg: the register pool of a CTA is what its own warps release, and 576 threads at 112
+// Roles (threads = NWG * 128 + 32 + NWG * 32): warpgroups 0..NWG-1 softmax; warp 4 NWG = TMA producer; warps 4 NWG + 1 + g =
+// single-thread tcgen05.mma issuer of warpgroup g.  (No setmaxnreg: the register pool of a CTA is what its own warps release, and 576 threads at 112
 // registers already use the whole file.)
 //
 // TMEM columns per warpgroup g (base 160 g): [0, 64) = S buffer 0, [64, 128) = S buffer 1, [128, 160) = O_g.  S_g(t) lands
@@ -59,6 +59,26 @@ namespace {
 #else
 #define A2_STTM(stmt) stmt
 #endif
+#ifdef GRL_A2_DIAG_NOPV
+#define A2_PV(stmt)
+#else
+#define A2_PV(stmt) stmt
+#endif
+#ifdef GRL_A2_DIAG_NOQK
+#define A2_QK(stmt)
+#else
+#define A2_QK(stmt) stmt
+#endif
+#ifdef GRL_A2_DIAG_NOKVCOMMIT
+#define A2_KVCOMMIT(bar) mbar_arrive(bar)
+#else
+#define A2_KVCOMMIT(bar) umma_commit(bar)
+#endif
+#ifdef GRL_A2_DIAG_ONEBOX  // the producer issues ONE box per Q / K / V tile (garbage data): what does TMA issue cost?
+#define A2_BOXCNT(cnt, bw) min((cnt), (bw))
+#else
+#define A2_BOXCNT(cnt, bw) (cnt)
+#endif
 #ifdef GRL_A2_DIAG_NOMAX
 #define A2_MAX(expr) 0.f
 #else
@@ -66,26 +86,33 @@ namespace {
 #endif
 
 constexpr int kKT2 = 64;       // keys per tile
-constexpr int kStages2 = 5;    // K / V ring depth (tiles t .. t+2 are live in the MMA pipeline, the rest is prefetch)
 constexpr float kTau = 8.0f;   // lazy-rescale threshold (log2 units): P <= 2^8 stays far inside fp16 / bf16 range
 constexpr int kColsPerWg = 160;  // TMEM columns per warpgroup: S buffer 0 | S buffer 1 | O
 
+constexpr int kMaxStages2 = 16;
+
+// Shared memory (bytes): [Q tiles NWG x 8 KB][barriers 1 KB][koff / rid 8 KB][K ring NS x 4 KB][V ring NS x 4 KB][bias table].
+// The ring depth NS is chosen at launch from what is left of the 227 KB: tiles t .. t+2 are live in the MMA pipeline, the
+// rest is prefetch distance -- a K / V tile comes from HBM / L2 through TMA in ~1.6 us, so a shallow ring bounds the
+// whole kernel by that latency (measured: 5 stages -> every variant of the kernel, even one without any math, took ~1 ms).
 template <int NWG>
 struct A2Smem {
   static constexpr int Q_BYTES = kQT * 64;
   static constexpr int KV_BYTES = kKT2 * 64;
-  static constexpr int OFF_K = NWG * Q_BYTES;
-  static constexpr int OFF_V = OFF_K + kStages2 * KV_BYTES;
-  static constexpr int OFF_META = OFF_V + kStages2 * KV_BYTES;  // int koff[kStages2][KT], krid[kStages2][KT]
-  static constexpr int OFF_BAR = OFF_META + kStages2 * 2 * kKT2 * 4;
-  static constexpr int OFF_BIAS = OFF_BAR + 512;  // optional: the head's 4-copy bias table (16 bytes per table row)
-  static constexpr int TOTAL = OFF_BIAS + 1024;   // + 16 * rows_pad when the table is staged
+  static constexpr int OFF_BAR = NWG * Q_BYTES;
+  static constexpr int OFF_META = OFF_BAR + 1024;                            // int koff[16][KT], krid[16][KT]
+  static constexpr int OFF_K = OFF_META + kMaxStages2 * 2 * kKT2 * 4;
+  static constexpr int FIXED = OFF_K + 1024;                                 // + alignment slack
+  __host__ __device__ static constexpr int off_v(int ns) { return OFF_K + ns * KV_BYTES; }
+  __host__ __device__ static constexpr int off_bias(int ns) { return OFF_K + 2 * ns * KV_BYTES; }
+  __host__ __device__ static constexpr int total(int ns, int bias_bytes) { return FIXED + 2 * ns * KV_BYTES + bias_bytes; }
 };
 
 struct A2Geom {
   int bw_q, bw_k;   // tokens per TMA box
   int n_qg;         // query groups (NWG * 128 rows) per window
   int per_head;     // B * windows * n_qg work items per head; CTA b works on head b / (gridDim / heads)
+  int stages;       // K / V ring depth
 };
 
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
@@ -112,13 +139,25 @@ __device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64
 }
 
 // Lean mbarrier wait: mbarrier.try_wait suspends the thread in hardware until the phase completes or a system time limit
-// passes, so the retry loop is two instructions; a wall-clock bound (checked every 4096 retries) turns a protocol bug into
-// a trap instead of a hung GPU.
-__device__ __forceinline__ void mbar_wait2(uint64_t* bar, uint32_t parity) {
+// passes, so the retry loop is two instructions.  A wall-clock bound (checked every 4096 retries) turns a protocol bug into
+// a recorded diagnosis instead of a hung GPU: the first waiter that times out writes (site, block, warp, parity) to
+// g_a2_dbg and raises an abort flag; every wait then falls through, the kernel finishes with garbage and the host can
+// read the record (grl_tc_attn2_debug).
+__device__ int g_a2_dbg[8];
+__device__ __forceinline__ void mbar_wait2(uint64_t* bar, uint32_t parity, int site = 0) {
   uint32_t ok;
   int spins = 0;
   long long t0 = 0;
   for (;;) {
+#ifdef GRL_A2_SPIN  // A/B: non-blocking test_wait in a spin loop instead of the hardware-suspended try_wait
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+#else
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
@@ -126,13 +165,42 @@ __device__ __forceinline__ void mbar_wait2(uint64_t* bar, uint32_t parity) {
         : "=r"(ok)
         : "r"(smem_u32(bar)), "r"(parity)
         : "memory");
+#endif
     if (ok) return;
     if ((++spins & 4095) == 0) {
+      if (*reinterpret_cast<volatile int*>(&g_a2_dbg[0]) != 0) return;  // somebody timed out: drain
       const long long now = clock64();
       if (t0 == 0) t0 = now;
-      else if (now - t0 > 4000000000ll) __trap();
+      else if (now - t0 > 1000000000ll) {
+        if (atomicCAS(&g_a2_dbg[0], 0, 1) == 0) {
+          g_a2_dbg[1] = site, g_a2_dbg[2] = blockIdx.x, g_a2_dbg[3] = threadIdx.x >> 5, g_a2_dbg[4] = (int)parity;
+          g_a2_dbg[5] = (int)(smem_u32(bar) & 0xffff);
+          __threadfence();
+        }
+        return;
+      }
     }
   }
+}
+
+// Warp-collective wait (call sites are warp-uniform).
+__device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity, int site = 0) {
+#ifdef GRL_A2_ONE_LANE_POLL  // measured slightly slower than letting every lane poll (the warp instruction is one request)
+  if ((threadIdx.x & 31) == 0) mbar_wait2(bar, parity, site);
+  __syncwarp();
+#else
+  mbar_wait2(bar, parity, site);
+#endif
+}
+
+// Waits of the producer / issuer warps: they are off the softmax warps' critical path (deep K / V ring, S two tiles ahead),
+// so they may sleep in hardware (try_wait with a suspend-time hint) instead of polling next to the warps doing the math.
+__device__ __forceinline__ void mbar_wait_bg(uint64_t* bar, uint32_t parity, int site = 0) {
+#ifdef GRL_A2_BG_SLEEP
+  mbar_wait(bar, parity);
+#else
+  mbar_wait2(bar, parity, site);
+#endif
 }
 
 // shared-memory loads by 32-bit shared address (the tile base is aligned through integer arithmetic, after which the
@@ -163,31 +231,46 @@ struct Item {
   int qg, h, bw, b, wr, wc, nact;
 };
 
+// position in the K / V ring: stage and the parity of the fill that is current for it
+struct Ring {
+  int st;
+  uint32_t ph;
+  __device__ __forceinline__ void adv(int ns) {
+    if (++st == ns) st = 0, ph ^= 1u;
+  }
+  __device__ __forceinline__ void skip(int n, int ns) {  // n tiles at once (a warpgroup sitting an item out)
+    const int tot = st + n;
+    ph ^= (uint32_t)(tot / ns) & 1u;
+    st = tot % ns;
+  }
+};
+
 template <int NWG, int KW, int VAR, bool BS>
-__global__ void __launch_bounds__(NWG * 128 + 64, 1)
+__global__ void __launch_bounds__(NWG * 128 + 32 + NWG * 32, 1)
 attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
              const __grid_constant__ CUtensorMap tmV, const AttnTcArgs a, const A2Geom tg) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   using S = A2Smem<NWG>;
   constexpr int KT = kKT2;
+  const int NS = tg.stages;
   uint8_t* Qs = smem;
   uint8_t* Ks = smem + S::OFF_K;
-  uint8_t* Vs = smem + S::OFF_V;
-  int* koff_s = reinterpret_cast<int*>(smem + S::OFF_META);  // [kStages2][KT]
-  int* krid_s = koff_s + kStages2 * KT;                       // [kStages2][KT]
+  uint8_t* Vs = smem + S::off_v(NS);
+  int* koff_s = reinterpret_cast<int*>(smem + S::OFF_META);  // [16][KT]
+  int* krid_s = koff_s + kMaxStages2 * KT;                    // [16][KT]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::OFF_BAR);
   uint64_t* q_full = bars;                  // [NWG]  Q tile of warpgroup g landed            (TMA tx)
   uint64_t* q_empty = q_full + 4;           // [NWG]  every Q K^T of the item that reads it is done  (tcgen05.commit)
-  uint64_t* bar_s = q_empty + 4;            // [NWG][2]  S_g(t) ready in buffer t & 1            (tcgen05.commit)
-  uint64_t* p_full = bar_s + 8;             // [NWG]  P_g(t) written to TMEM                     (4 warp arrivals)
-  uint64_t* o_done = p_full + 4;            // [NWG]  P V_g(t) complete, every tile (rescale of O / final O)  (tcgen05.commit)
-  uint64_t* kv_full = o_done + 4;           // [kStages2]  K_t, V_t landed                       (TMA tx)
-  uint64_t* kv_empty = kv_full + 8;         // [kStages2]  every MMA that reads the stage is done (tcgen05.commit)
-  uint64_t* meta_full = kv_empty + 8;       // [kStages2]  koff / rid of the stage written      (32 arrivals)
-  uint64_t* bias_full = meta_full + 8;      // the head's bias table landed in shared memory (BS)   (bulk-copy tx)
+  uint64_t* bar_s = q_empty + 4;            // [NWG][2]  buffer t & 1: S_g(t) ready / P V_g(t-2) done; every tile commits once
+  uint64_t* p_full = bar_s + 8;             // [NWG][2]  P_g(t) written to TMEM, buffer t & 1    (4 warp arrivals)
+  uint64_t* item_done = p_full + 8;         // [NWG]  warpgroup g has consumed the item's closing completions (4 warp arrivals)
+  uint64_t* kv_full = item_done + 4;           // [NS]  K_t, V_t landed                       (TMA tx)
+  uint64_t* kv_empty = kv_full + kMaxStages2;  // [NS]  every MMA that reads the stage is done (tcgen05.commit)
+  uint64_t* meta_full = kv_empty + kMaxStages2;  // [NS]  koff / rid of the stage written      (32 arrivals)
+  uint64_t* bias_full = meta_full + kMaxStages2;      // the head's bias table landed in shared memory (BS)   (bulk-copy tx)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bias_full + 1);
-  float* bias_s = reinterpret_cast<float*>(smem + S::OFF_BIAS);
+  float* bias_s = reinterpret_cast<float*>(smem + S::off_bias(NS));
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int wg = warp >> 2;
@@ -207,13 +290,14 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
       mbar_init(&q_empty[g], 1);
       mbar_init(&bar_s[2 * g], 1);
       mbar_init(&bar_s[2 * g + 1], 1);
-      mbar_init(&p_full[g], 4);
-      mbar_init(&o_done[g], 1);
+      mbar_init(&p_full[2 * g], 4);
+      mbar_init(&p_full[2 * g + 1], 4);
+      mbar_init(&item_done[g], 4);
     }
-    for (int s = 0; s < kStages2; ++s) {
+    for (int s = 0; s < NS; ++s) {
       mbar_init(&kv_full[s], 1);
-      mbar_init(&kv_empty[s], 1);
-      mbar_init(&meta_full[s], 32);
+      mbar_init(&kv_empty[s], NWG);
+      mbar_init(&meta_full[s], 1);
     }
     mbar_init(bias_full, 1);
     mbar_init_fence();
@@ -245,25 +329,34 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
     return it;
   };
 
-  if (wg == NWG) {
+  if (warp >= 4 * NWG) {
     if (warp == 4 * NWG) {
       // =============================================================== TMA producer
       // A run of `bw` consecutive tokens of one window row is contiguous in the (B, H, W, C) tensor even after the
       // roll (bw divides gcd(window width, shift)), so it is ONE 4-D box (32 channels x bw x 1 x 1) that lands as bw
       // rows of 64 bytes, 64-byte swizzled by the copy engine -- the layout the UMMA descriptors below expect.
-      auto tma_rows = [&](const CUtensorMap* map, const GrlGrid& g, const Item& it, int coff, uint8_t* dst, int n0,
-                          int cnt, int bw, uint64_t* bar) {
-        for (int s = lane; s * bw < cnt; s += 32) {
-          const int n = n0 + s * bw;
-          const int ih = n / g.ww, iw = n - ih * g.ww;
-          int y = it.wr * g.wh + ih + g.sh;
+      // ONE lane issues every box, with running (row, column) coordinates: per-lane coordinates would make the compiler
+      // serialise the warp into an elect / broadcast loop around each UTMALDG, and this warp -- not the tensor or the MUFU
+      // pipe -- was what bounded an earlier version of the kernel (~2000 cycles per key tile).
+      struct Cur {
+        int ih, iw;
+      };
+      auto tma_run = [&](const CUtensorMap* m1, int c1, uint8_t* d1, const CUtensorMap* m2, int c2, uint8_t* d2,
+                         const GrlGrid& g, const Item& it, Cur& cur, int cnt, int bw, uint64_t* bar) {  // lane 0
+        const int yb = it.wr * g.wh + g.sh, xb = it.wc * g.ww + g.sw;
+        for (int n = 0; n < A2_BOXCNT(cnt, bw); n += bw) {
+          int y = yb + cur.ih, x = xb + cur.iw;
           if (y >= g.H) y -= g.H;
-          int x = it.wc * g.ww + iw + g.sw;
           if (x >= g.W) x -= g.W;
-          tma_load_4d(dst + s * bw * 64, map, bar, coff, x, y, it.b);
+          tma_load_4d(d1 + n * 64, m1, bar, c1, x, y, it.b);
+          if (m2) tma_load_4d(d2 + n * 64, m2, bar, c2, x, y, it.b);
+          cur.iw += bw;
+          if (cur.iw >= g.ww) cur.iw = 0, ++cur.ih;
         }
       };
+      const bool mask_fast_p = (KW > 0) && (a.gk.sw == 0 || ((a.gk.ww - a.gk.sw) & 3) == 0);
       uint32_t kv_it = 0, q_cnt[NWG];
+      Ring rp = {0, 0};
 #pragma unroll
       for (int g = 0; g < NWG; ++g) q_cnt[g] = 0;
       if (BS && lane == 0) {  // the head's table: 4 shifted copies, contiguous in global memory, one bulk copy
@@ -277,18 +370,22 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
 #pragma unroll
         for (int g = 0; g < NWG; ++g) {
           if (g < it.nact) {
-            mbar_wait2(&q_empty[g], (q_cnt[g] & 1) ^ 1);
+            mbar_wait_bg(&q_empty[g], (q_cnt[g] & 1) ^ 1, 1);
             ++q_cnt[g];
             const int q0 = (it.qg * NWG + g) * kQT;
             const int cnt = min(kQT, Nq - q0);
-            if (lane == 0) mbar_expect_tx(&q_full[g], (uint32_t)cnt * 64u);
+            if (lane == 0) {
+              mbar_expect_tx(&q_full[g], (uint32_t)A2_BOXCNT(cnt, tg.bw_q) * 64u);
+              Cur cq = {q0 / a.gq.ww, q0 % a.gq.ww};
+              tma_run(&tmQ, a.q_off + it.h * kDP, Qs + g * S::Q_BYTES, nullptr, 0, nullptr, a.gq, it, cq, cnt, tg.bw_q, &q_full[g]);
+            }
             __syncwarp();
-            tma_rows(&tmQ, a.gq, it, a.q_off + it.h * kDP, Qs + g * S::Q_BYTES, q0, cnt, tg.bw_q, &q_full[g]);
           }
         }
-        for (int t = 0; t < ntiles; ++t, ++kv_it) {
-          const int st = kv_it % kStages2;
-          mbar_wait2(&kv_empty[st], ((kv_it / kStages2) & 1) ^ 1);
+        Cur ck = {0, 0};  // in-window (row, column) of the first key of the next tile
+        for (int t = 0; t < ntiles; ++t, ++kv_it, rp.adv(NS)) {
+          const int st = rp.st;
+          mbar_wait_bg(&kv_empty[st], rp.ph ^ 1, 2);
           const int k0 = t * KT, cnt = min(KT, Nk - k0);
           uint8_t* kd = Ks + st * S::KV_BYTES;
           uint8_t* vd = Vs + st * S::KV_BYTES;
@@ -297,7 +394,7 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
             fence_proxy_async_smem();
           }
           // koff / rid of the keys: read by the generic bias path (ragged tile, KW == 0) and by the shift mask
-          if (need_mask || KW == 0 || cnt < KT) {
+          if ((need_mask && !mask_fast_p) || KW == 0 || cnt < KT) {
             for (int r = lane; r < KT; r += 32) {
               const int kj = k0 + r;
               const Tok tk = locate(a.gk, it.wr, it.wc, kj < Nk ? kj : 0);
@@ -305,85 +402,96 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
               krid_s[st * KT + r] = region_id(a.gk, tk.r, tk.c);
             }
           }
-          mbar_arrive(&meta_full[st]);
-          if (lane == 0) mbar_expect_tx(&kv_full[st], (uint32_t)(cnt + (a.v_dense ? KT : cnt)) * 64u);
-          __syncwarp();
-          tma_rows(&tmK, a.gk, it, a.k_off + it.h * kDP, kd, k0, cnt, tg.bw_k, &kv_full[st]);
-          if (a.v_dense) {  // (B_, heads, Nk, 32) rows: one 2-D box (rows past this head's Nk: next head / zero fill, P == 0)
-            if (lane == 0) tma_load_2d(vd, &tmV, &kv_full[st], 0, (int)(((long long)it.bw * a.heads + it.h) * Nk + k0));
-          } else {
-            tma_rows(&tmV, a.gk, it, a.v_off + it.h * kDP, vd, k0, cnt, tg.bw_k, &kv_full[st]);
+          __syncwarp();  // every lane's koff / rid stores are ordered before lane 0's release
+          if (lane == 0) mbar_arrive(&meta_full[st]);
+          if (lane == 0) {
+            mbar_expect_tx(&kv_full[st], (uint32_t)(A2_BOXCNT(cnt, tg.bw_k) + (a.v_dense ? KT : A2_BOXCNT(cnt, tg.bw_k))) * 64u);
+            if (a.v_dense) {  // V = (B_, heads, Nk, 32) rows: one 2-D box (rows past this head's Nk: next head / zero fill, P == 0)
+              tma_run(&tmK, a.k_off + it.h * kDP, kd, nullptr, 0, nullptr, a.gk, it, ck, cnt, tg.bw_k, &kv_full[st]);
+              tma_load_2d(vd, &tmV, &kv_full[st], 0, (int)(((long long)it.bw * a.heads + it.h) * Nk + k0));
+            } else {  // K and V rows of a token sit in the same tensor: same coordinates, two channel offsets
+              tma_run(&tmK, a.k_off + it.h * kDP, kd, &tmV, a.v_off + it.h * kDP, vd, a.gk, it, ck, cnt, tg.bw_k, &kv_full[st]);
+            }
           }
+          __syncwarp();
         }
       }
-    } else if (warp == 4 * NWG + 1) {
-      // =============================================================== MMA issuer (one thread)
+    } else if (warp <= 4 * NWG + NWG) {
+      // =============================================================== MMA issuers: one warp (one thread) per warpgroup.
+      // Each issuer owns the MMAs of ONE warpgroup (the ordering the S / P aliasing needs is within a warpgroup); all of
+      // them release the K / V stages (kv_empty counts NWG).  After EVERY tile t the issuer commits to bar_s[t & 1]:
+      // that completion means "P V(t) done and, if it exists, S(t+2) ready".  The softmax warps consume these completions
+      // strictly in order per buffer, so every parity wait is exact; the two completions past the last tile are the
+      // "O final" signal.  Nothing on the softmax warps' critical path waits for an MMA that was issued in the same tile.
+      const int g = warp - (4 * NWG + 1);
       const uint32_t idesc_qk = umma_idesc(kQT, KT, fmt, 0, 0);
       const uint32_t idesc_pv = umma_idesc(kQT, kDP, fmt, 0, 1);
-      uint32_t kv_it = 0, q_cnt[NWG], p_cnt[NWG];
-#pragma unroll
-      for (int g = 0; g < NWG; ++g) q_cnt[g] = 0, p_cnt[g] = 0;
-      auto issue_qk = [&](int g, int st, int buf, bool last) {
-        const uint32_t q_sa = smem_u32(Qs + g * S::Q_BYTES), k_sa = smem_u32(Ks + st * S::KV_BYTES);
-#pragma unroll
-        for (int k = 0; k < kDP / 16; ++k)
-          umma_ss(tmem + g * kColsPerWg + buf * 64, umma_desc(q_sa + k * 32, 16, 512, SWZ_64B),
-                  umma_desc(k_sa + k * 32, 16, 512, SWZ_64B), idesc_qk, k != 0);
+      // descriptors: only the 14-bit start-address field (16-byte units) changes between uses
+      const uint64_t q_desc = umma_desc(smem_u32(Qs + g * S::Q_BYTES), 16, 512, SWZ_64B);
+      const uint64_t k_desc0 = umma_desc(smem_u32(Ks), 16, 512, SWZ_64B);
+      const uint64_t v_desc0 = umma_desc(smem_u32(Vs), 16, 512, SWZ_64B);
+      const uint32_t wg_ta = tmem + g * kColsPerWg;
+      uint32_t kv_it = 0, q_cnt = 0, p_cnt[2] = {0, 0}, d_cnt = 0;
+      Ring r0 = {0, 0}, r2 = {0, 0}, rl = {0, 0};  // tile t, tile t + 2, last tile handled
+      r2.adv(NS);
+      r2.adv(NS);
+      auto issue_qk = [&](int st, int buf, bool last) {  // lane 0
+        const uint64_t kd = k_desc0 + (uint64_t)(st * (S::KV_BYTES >> 4));
+        A2_QK(umma_ss(wg_ta + buf * 64, q_desc, kd, idesc_qk, false));
+        A2_QK(umma_ss(wg_ta + buf * 64, q_desc + 2, kd + 2, idesc_qk, true));
         if (last) umma_commit(&q_empty[g]);
-        umma_commit(&bar_s[2 * g + buf]);
       };
       for (int item = my_c; item < tg.per_head; item += cph) {
         const Item it = decode(item);
-        // prologue: S_g(0) and S_g(1)
-        for (int t0 = 0; t0 < 2 && t0 < ntiles; ++t0) {
-          const int st = (kv_it + t0) % kStages2;
-          mbar_wait2(&kv_full[st], ((kv_it + t0) / kStages2) & 1);
-#pragma unroll
-          for (int g = 0; g < NWG; ++g) {
-            if (g < it.nact) {
-              if (t0 == 0) {
-                mbar_wait2(&q_full[g], q_cnt[g] & 1);
-                ++q_cnt[g];
-              }
-              if (lane == 0) {
-                tcgen05_fence_after();
-                issue_qk(g, st, t0, t0 + 1 == ntiles);
-              }
-              __syncwarp();
-            }
-          }
+        const bool active = g < it.nact;
+        if (active) {
+          mbar_wait_bg(&q_full[g], q_cnt & 1, 3);
+          ++q_cnt;
         }
-        for (int t = 0; t < ntiles; ++t, ++kv_it) {
-          const int st = kv_it % kStages2, st2 = (kv_it + 2) % kStages2;
-          if (t + 2 < ntiles) mbar_wait2(&kv_full[st2], ((kv_it + 2) / kStages2) & 1);
-#pragma unroll
-          for (int g = 0; g < NWG; ++g) {
-            if (g < it.nact) {
-              mbar_wait2(&p_full[g], p_cnt[g] & 1);
-              ++p_cnt[g];
-              if (lane == 0) {
-                tcgen05_fence_after();
-                const uint32_t v_sa = smem_u32(Vs + st * S::KV_BYTES);
-                const uint32_t wg_ta = tmem + g * kColsPerWg;
-                const uint32_t p_ta = wg_ta + (t & 1) * 64;
-#pragma unroll
-                for (int k = 0; k < KT / 16; ++k)
-                  umma_ts(wg_ta + 128, p_ta + k * 8, umma_desc(v_sa + k * 1024, 16, 512, SWZ_64B), idesc_pv, (t | k) != 0);
-                umma_commit(&o_done[g]);
-                if (t + 2 < ntiles) issue_qk(g, st2, t & 1, t + 3 == ntiles);
-              }
-              __syncwarp();
-            }
+        // prologue: S_g(0) and S_g(1)
+        Ring rq = r0;  // ring position of tile t0
+        for (int t0 = 0; t0 < 2 && t0 < ntiles; ++t0, rq.adv(NS)) {
+          const int st = rq.st;
+          mbar_wait_bg(&kv_full[st], rq.ph, 4);
+          if (active && lane == 0) {
+            tcgen05_fence_after();
+            issue_qk(st, t0, t0 + 1 == ntiles);
+            umma_commit(&bar_s[2 * g + t0]);
           }
-          if (lane == 0) umma_commit(&kv_empty[st]);
           __syncwarp();
         }
+        if (ntiles == 1 && active && lane == 0) umma_commit(&bar_s[2 * g + 1]);  // keep both buffers' counts in step
+        __syncwarp();
+        for (int t = 0; t < ntiles; ++t, ++kv_it, rl = r0, r0.adv(NS), r2.adv(NS)) {
+          const int st = r0.st, st2 = r2.st;
+          if (t + 2 < ntiles) mbar_wait_bg(&kv_full[st2], r2.ph, 5);
+          if (active) {
+            // (per S buffer: the softmax warps run up to two tiles ahead of this thread, and an mbarrier that completes
+            // twice before its waiter has looked is indistinguishable from one that has not completed)
+            mbar_wait_bg(&p_full[2 * g + (t & 1)], p_cnt[t & 1] & 1, 6);
+            ++p_cnt[t & 1];
+            if (lane == 0) {
+              tcgen05_fence_after();
+              const uint64_t vd = v_desc0 + (uint64_t)(st * (S::KV_BYTES >> 4));
+              const uint32_t p_ta = wg_ta + (t & 1) * 64;
+#pragma unroll
+              for (int k = 0; k < KT / 16; ++k) A2_PV(umma_ts(wg_ta + 128, p_ta + k * 8, vd + (uint64_t)(k * 64), idesc_pv, (t | k) != 0));
+              if (t + 2 < ntiles) issue_qk(st2, t & 1, t + 3 == ntiles);
+              umma_commit(&bar_s[2 * g + (t & 1)]);  // P V(t) done (+ S(t+2) ready)
+              A2_KVCOMMIT(&kv_empty[st]);            // every MMA of this warpgroup that reads stage st has been issued
+            }
+          } else if (lane == 0) {
+            mbar_arrive(&kv_empty[st]);  // sitting this item out: release the stage (after its fill: kv_full(st2) / prologue waits)
+          }
+          __syncwarp();
+        }
+        if (active) {  // the warpgroup has consumed this item's closing completions of bar_s (see its epilogue)
+          mbar_wait_bg(&item_done[g], d_cnt & 1, 7);
+          ++d_cnt;
+        }
       }
-      // every commit has arrived before the CTA's shared memory goes away
-      if (kv_it > 0) {
-        const uint32_t last = kv_it - 1;
-        mbar_wait2(&kv_empty[last % kStages2], (last / kStages2) & 1);
-      }
+      // every commit has arrived before the CTA's shared memory goes away (kv_empty needs all NWG issuers)
+      if (kv_it > 0) mbar_wait_bg(&kv_empty[rl.st], rl.ph, 8);
     }
   } else {
     // =============================================================== softmax warpgroups: thread = query row
@@ -392,11 +500,12 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
     const uint32_t to = ts0 + 128;                                                        // O columns
     bool bias_ready = false;
     const uint32_t bias_sa = smem_u32(bias_s), koff_sa = smem_u32(koff_s), krid_sa = smem_u32(krid_s);
-    uint32_t s_cnt[2] = {0, 0}, o_cnt = 0, kv_it = 0;  // completions consumed: bar_s[buf], o_done (one per tile)
+    uint32_t s_cnt[2] = {0, 0};  // completions consumed per S buffer (every tile consumes exactly one)
+    Ring rs = {0, 0};
     for (int item = my_c; item < tg.per_head; item += cph) {
       const Item it = decode(item);
       if (wg >= it.nact) {
-        kv_it += ntiles;
+        rs.skip(ntiles, NS);
         continue;
       }
       const int qi = (it.qg * NWG + wg) * kQT + row;
@@ -404,7 +513,7 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
       const Tok tq = locate(a.gq, it.wr, it.wc, q_ok ? qi : it.qg * NWG * kQT);
       const float* bias_h = a.bias + (size_t)it.h * 4 * a.rows_pad;
       if (BS && !bias_ready) {
-        mbar_wait2(bias_full, 0);
+        mbar_wait_warp(bias_full, 0, 9);
         bias_ready = true;
       }
       const int base_i = (tq.ih + a.gk.wh - 1) * Wt + tq.iw + a.gk.ww - 1;
@@ -419,8 +528,8 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
       const bool mask_fast = (KW > 0) && (a.gk.sw == 0 || ((a.gk.ww - a.gk.sw) & 3) == 0);
       float m_ref = 0.f, l_run = 0.f;
 
-      for (int t = 0; t < ntiles; ++t, ++kv_it) {
-        const int k0 = t * KT, st = kv_it % kStages2, buf = t & 1;
+      for (int t = 0; t < ntiles; ++t, rs.adv(NS)) {
+        const int k0 = t * KT, st = rs.st, buf = t & 1;
         const uint32_t ts = ts0 + buf * 64;
         const bool full_tile = (KW > 0) && (k0 + KT <= Nk);
         // ---- x = bias (+ mask) - m_ref first: these loads and adds do not depend on S and run while Q K^T is in flight.
@@ -454,11 +563,11 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
           }
         }
         // ---- S_t
-        mbar_wait2(&bar_s[2 * wg + buf], s_cnt[buf] & 1);
+        mbar_wait_warp(&bar_s[2 * wg + buf], s_cnt[buf] & 1, 10);
         ++s_cnt[buf];
         tcgen05_fence_after();
         const bool meta_mask = need_mask && !(full_tile && mask_fast);
-        if (!full_tile || meta_mask) mbar_wait2(&meta_full[st], (kv_it / kStages2) & 1);  // S_t ready => this fill is the current one
+        if (!full_tile || meta_mask) mbar_wait_warp(&meta_full[st], rs.ph, 11);  // S_t ready => this fill is the current one
         if (!full_tile) {
 #pragma unroll
           for (int j = 0; j < KT; ++j) x[j] = (BS ? lds32f(bias_sa + 4u * (uint32_t)(base_i - lds32i(koff_sa + 4u * (st * KT + j))))
@@ -492,19 +601,18 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
         const float mx = A2_MAX(fmax3(mx0, mx1, fmaxf(x[KT - 2], x[KT - 1])));
         // ---- lazy rescale: move the reference only when a row outgrew it by 2^kTau (always on the first tile)
         const bool first = (t == 0);
-        // P V_g(t-1) complete (o_done completes once per tile; consuming EVERY completion, in order, keeps the parity waits
-        // exact -- a parity wait cannot tell phases two apart).  It was issued a whole S-load + max ago: normally no wait.
-        if (!first) {
-          mbar_wait2(&o_done[wg], (o_cnt + t - 1) & 1);
-          tcgen05_fence_after();
-        }
         if (__any_sync(0xffffffffu, first || mx > kTau)) {
           float delta = first ? mx : fmaxf(mx, 0.f);
           if (!(fabsf(delta) < 1e30f)) delta = 0.f;  // rows of a partial query tile hold garbage
           m_ref += delta;
 #pragma unroll
           for (int j = 0; j < KT; ++j) x[j] -= delta;
-          if (!first) {  // O_g holds P V of tiles < t (P V(t-1) complete: waited for above)
+          if (!first) {
+            // O_g must hold P V of every tile < t.  The NEXT completion of the other buffer's barrier (S(t+1) ready, or the
+            // closing completion when t is the last tile) is committed right after P V(t-1): peek at it (the wait at tile
+            // t+1 / in the epilogue consumes it), which keeps the wait exact and off the common path.
+            mbar_wait_warp(&bar_s[2 * wg + (buf ^ 1)], s_cnt[buf ^ 1] & 1, 12);
+            tcgen05_fence_after();
             const float sc = ex2(-delta);
             uint32_t v[32];
             tmem_ld32(to, v);
@@ -529,11 +637,18 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
         tmem_st_wait();
         tcgen05_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&p_full[wg]);
+        if (lane == 0) mbar_arrive(&p_full[2 * wg + buf]);
       }
       // ---- epilogue: O_g final
-      mbar_wait2(&o_done[wg], (o_cnt + ntiles - 1) & 1);
-      o_cnt += ntiles;
+      // closing completions: buffer ntiles & 1 (P V(ntiles-2) done), then buffer (ntiles+1) & 1 (P V(ntiles-1) done = O final)
+      mbar_wait_warp(&bar_s[2 * wg + (ntiles & 1)], s_cnt[ntiles & 1] & 1, 13);
+      ++s_cnt[ntiles & 1];
+      mbar_wait_warp(&bar_s[2 * wg + ((ntiles + 1) & 1)], s_cnt[(ntiles + 1) & 1] & 1, 14);
+      ++s_cnt[(ntiles + 1) & 1];
+      // "item consumed": the issuer may now commit the next item's S(0) / S(1) to these barriers (an mbarrier must not
+      // complete twice before its waiter has looked: a parity wait cannot tell phases two apart)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&item_done[wg]);
       tcgen05_fence_after();
       {
         uint32_t v[32];
@@ -612,18 +727,6 @@ int make_dense_map2(CUtensorMap* m, const void* base, long long rows, int box_ro
   return GRL_OK;
 }
 
-int sm_count() {
-  static int n[16] = {0};
-  int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return 148;
-  if (n[dev] == 0) {
-    int v = 0;
-    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
-    n[dev] = v;
-  }
-  return n[dev];
-}
-
 constexpr int kMaxSmem = 232448;  // 227 KB: the per-CTA shared-memory limit of sm_100
 
 template <int NWG, int KW, int VAR, bool BS>
@@ -634,7 +737,7 @@ int launch2_var(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap&
   int dev = 0;
   GRL_CUDA(cudaGetDevice(&dev));
   if (dev < 0 || dev >= kMaxDevices || !configured[dev]) {
-    GRL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, BS ? kMaxSmem : A2Smem<NWG>::TOTAL));
+    GRL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
     if (dev >= 0 && dev < kMaxDevices) configured[dev] = true;
   }
   const int Nq = a.gq.wh * a.gq.ww;
@@ -644,8 +747,11 @@ int launch2_var(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap&
   tg.per_head = (int)per_head;
   const long long cph = std::max(1ll, std::min((long long)(sm_count() / a.heads), per_head));  // CTAs per head
   const unsigned grid = (unsigned)(cph * a.heads);
-  const int smem = A2Smem<NWG>::TOTAL + (BS ? 16 * a.rows_pad : 0);
-  kern<<<grid, NWG * 128 + 64, smem, st>>>(tq, tk, tv, a, tg);
+  const int bias_bytes = BS ? 16 * a.rows_pad : 0;
+  tg.stages = std::min(kMaxStages2, (kMaxSmem - A2Smem<NWG>::FIXED - bias_bytes) / (2 * A2Smem<NWG>::KV_BYTES));
+  GRL_REQUIRE(tg.stages >= 4, "attn2: no room for the K / V ring");
+  const int smem = A2Smem<NWG>::total(tg.stages, bias_bytes);
+  kern<<<grid, NWG * 128 + 32 + NWG * 32, smem, st>>>(tq, tk, tv, a, tg);
   GRL_LAUNCH_CHECK("attn2_kernel");
   return GRL_OK;
 }
@@ -656,7 +762,10 @@ int launch2_bs(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& 
   // the 4-copy table in shared memory when it fits next to the tiles: LDS.128 costs 4 wavefronts where the L1 path pays
   // ~7.5 tag lookups (the 128-byte runs of the four copies are not line aligned) -- the L1 data pipe was the busiest unit
   static const bool off = [] { const char* e = getenv("GRL_ATTN2_NO_SMEM_BIAS"); return e && e[0] == '1'; }();
-  if (KW > 0 && !off && A2Smem<NWG>::TOTAL + 16 * a.rows_pad <= kMaxSmem) return launch2_var<NWG, KW, VAR, (KW > 0)>(tq, tk, tv, a, tg, st);
+  // ... as long as the table leaves room for a ring deep enough to cover the TMA latency (>= min_ring stages)
+  static const int min_ring = [] { const char* e = getenv("GRL_ATTN2_MIN_RING"); return e ? atoi(e) : 8; }();
+  if (KW > 0 && !off && A2Smem<NWG>::total(min_ring, 16 * a.rows_pad) <= kMaxSmem)
+    return launch2_var<NWG, KW, VAR, (KW > 0)>(tq, tk, tv, a, tg, st);
   return launch2_var<NWG, KW, VAR, false>(tq, tk, tv, a, tg, st);
 }
 
@@ -683,7 +792,18 @@ int launch2_nwg(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap&
   }
 }
 
+int attn2_debug_read(int* out8) {
+  int tmp[8] = {0};
+  if (cudaMemcpyFromSymbol(tmp, g_a2_dbg, sizeof(tmp)) != cudaSuccess) return -1;
+  for (int i = 0; i < 8; ++i) out8[i] = tmp[i];
+  int zero[8] = {0};
+  cudaMemcpyToSymbol(g_a2_dbg, zero, sizeof(zero));
+  return 0;
+}
+
 }  // namespace
+
+int attn2_debug(int* out8) { return attn2_debug_read(out8); }
 
 // Returns GRL_OK after launching, a negative error, or +1 when this geometry cannot be expressed as TMA boxes (the
 // caller then launches the gather kernel of attn_tc.cu).  Arguments already validated by launch_attn_tc.

@@ -440,9 +440,11 @@ static int launch_attn_one(const AttnTcArgs& a, unsigned nblk, cudaStream_t st) 
 int attn_variant(int set) {
   static int variant = -1;
   if (variant < 0) {
+    // default 5: the persistent TMEM-resident kernel (attn2.cu) wherever the geometry has TMA boxes, this file's gather
+    // kernel otherwise.  GRL_ATTN_SPLIT=0 forces the gather kernel (A/B runs, tools/attn_debug.py).
     const char* e = getenv("GRL_ATTN_SPLIT");
-    const int v = e ? atoi(e) : 0;
-    variant = (v >= 1 && v <= 5) ? v : 0;
+    const int v = e ? atoi(e) : 5;
+    variant = (v >= 0 && v <= 5) ? v : 5;
   }
   const int prev = variant;
   if (set >= 0 && set <= 5) variant = set;

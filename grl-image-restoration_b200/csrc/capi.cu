@@ -236,6 +236,12 @@ int grl_tc_unpack16(const void* x, int64_t ldx, int x_off, float* y, int64_t ldy
   if (check_fmt(fmt)) return GRL_ERR_INVALID;
   return tc::launch_unpack_bf16(x, ldx, x_off, y, ldy, M, C, fmt, (cudaStream_t)stream);
 }
+int grl_tc_head_pack(const float* x, int B, int Cin, int H, int W, int Hp, int Wp, const float* mean4, float range, void* y16,
+                     int Cpad, float* y32, int fmt, void* stream) {
+  if (check_fmt(fmt)) return GRL_ERR_INVALID;
+  GRL_REQUIRE(x && y16, "head_pack: null argument");
+  return tc::launch_head_pack(x, B, Cin, H, W, Hp, Wp, mean4, range, y16, Cpad, y32, fmt, (cudaStream_t)stream);
+}
 int grl_tc_avgpool16(const void* x, void* y, int B, int H, int W, int Cpad, int df, int fmt, void* stream) {
   if (check_fmt(fmt)) return GRL_ERR_INVALID;
   return tc::launch_avgpool_bf16(x, y, B, H, W, Cpad, df, fmt, (cudaStream_t)stream);
@@ -273,6 +279,9 @@ int grl_tc_gemm(const GrlTcGemm* p, void* stream) {
   a.slot_scale = p->slot_scale;
   a.C = p->C, a.gamma = p->gamma, a.beta = p->beta, a.eps = p->eps, a.res_scale = p->res_scale;
   a.cab_y = p->cab_y, a.ld_caby = p->ld_caby, a.cab_gate = p->cab_gate, a.L = p->L;
+  a.ps_r = p->ps_r, a.out_nchw = p->out_nchw, a.nchw_r = p->nchw_r > 0 ? p->nchw_r : 1, a.Hc = p->Hc, a.Wc = p->Wc;
+  a.post_scale = p->post_scale;
+  for (int c = 0; c < 4; ++c) a.post_shift[c] = p->post_shift[c];
   GRL_REQUIRE(p->bias != nullptr, "tc_gemm: bias is required (pass zeros)");
   GRL_REQUIRE(p->n_store <= p->npad && p->n_real <= p->npad, "tc_gemm: n_store/n_real exceed npad");
   if (p->epi == tc::EPI_QKV) GRL_REQUIRE(p->slot_scale && p->out_bf16 && p->ldo_bf16 >= p->npad, "tc_gemm: QKV epilogue arguments");
@@ -308,6 +317,7 @@ int grl_tc_attn(const GrlTcAttn* p, void* stream) {
 }
 
 int grl_tc_attn_variant(int variant) { return tc::attn_variant(variant); }
+int grl_tc_attn2_debug(int* out8) { return tc::attn2_debug(out8); }
 
 int grl_psnr_f32(const float* restored, const float* target, int B, int C, int H, int W, int border, void* workspace,
                  size_t workspace_bytes, float* psnr_rgb, float* psnr_y, void* stream) {

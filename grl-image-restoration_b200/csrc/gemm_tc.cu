@@ -261,6 +261,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (a.res_f32 && n < a.N_f32) val += __ldg(a.res_f32 + tok * a.ldr + n);
           o[j] = (n < a.N) ? val : 0.f;
           if (a.out_f32 && n < a.N_f32) a.out_f32[tok * a.ldo_f32 + n] = o[j];
+          if (CONV && a.out_nchw && n < a.N_f32) {
+            // tail fusion: x / img_range + mean (grl.py:549), the crop (:551), channels-last -> bchw and, for the one-step
+            // head, PixelShuffle (upsample.py:33-50; torch order n = c r^2 + dy r + dx) folded into the store
+            const int r = a.nchw_r, rr = r * r;
+            const int c = n / rr, q = n - c * rr;
+            const int yy = (ty0 + row / kTW) * r + q / r, xx = (tx0 + row % kTW) * r + q % r;
+            if (yy < a.Hc && xx < a.Wc)
+              a.out_nchw[(((long long)tb * (a.N_f32 / rr) + c) * a.Hc + yy) * a.Wc + xx] = fmaf(o[j], a.post_scale, a.post_shift[c & 3]);
+          }
         }
         if (out16) {
 #pragma unroll
@@ -437,13 +446,31 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       epi_barrier();
       const int nvec = min((long long)ncols, a.ldo_bf16 - n0) >> 3;  // 16-byte vectors per row
       const int ew = et >> 5;
+      if (CONV && a.ps_r > 0) {
+        // PixelShuffle folded into the store (upsample.py:6-30): the weights are packed so that column n' = q * Cq + c
+        // holds torch's channel c r^2 + q, i.e. Cq consecutive columns are ONE output pixel's channels
+        const int ps = a.ps_r, Cq = a.N / (ps * ps);
+        const int nv = min(BN, a.N - n0) >> 3;
 #pragma unroll 4
-      for (int r = ew; r < kBM; r += 4) {
-        const long long tok = s_tok[r];
-        if (tok < 0) continue;
-        for (int vv = lane; vv < nvec; vv += 32)
-          if (GRL_GDIAG_ST16(true))
-            *reinterpret_cast<uint4*>(out16 + tok * a.ldo_bf16 + n0 + vv * 8) = *reinterpret_cast<const uint4*>(stg + r * P16 + vv * 8);
+        for (int r = ew; r < kBM; r += 4) {
+          if (s_tok[r] < 0) continue;
+          const int y = ty0 + r / kTW, x = tx0 + r % kTW;
+          for (int vv = lane; vv < nv; vv += 32) {
+            const int n = n0 + vv * 8;
+            const int q = n / Cq, c = n - q * Cq;
+            const long long dtok = ((long long)tb * a.H * ps + y * ps + q / ps) * ((long long)a.W * ps) + x * ps + q % ps;
+            *reinterpret_cast<uint4*>(out16 + dtok * a.ldo_bf16 + c) = *reinterpret_cast<const uint4*>(stg + r * P16 + vv * 8);
+          }
+        }
+      } else {
+#pragma unroll 4
+        for (int r = ew; r < kBM; r += 4) {
+          const long long tok = s_tok[r];
+          if (tok < 0) continue;
+          for (int vv = lane; vv < nvec; vv += 32)
+            if (GRL_GDIAG_ST16(true))
+              *reinterpret_cast<uint4*>(out16 + tok * a.ldo_bf16 + n0 + vv * 8) = *reinterpret_cast<const uint4*>(stg + r * P16 + vv * 8);
+        }
       }
     }
   }
@@ -521,6 +548,14 @@ int launch_gemm_tc(const GemmTcProblem& p, GemmTcArgs a, cudaStream_t st) {
   GRL_REQUIRE(p.epi != EPI_LN || p.npad <= 256, "gemm_tc: LayerNorm epilogue needs the whole row in one tile (N=%d)",
               p.npad);
   const bool conv = p.taps == 9;
+  if (a.ps_r > 0)
+    GRL_REQUIRE(conv && p.epi == EPI_BIAS_ACT && !a.out_f32 && !a.res_f32 && a.out_bf16 && a.N % (a.ps_r * a.ps_r) == 0 &&
+                    (a.N / (a.ps_r * a.ps_r)) % 8 == 0 && a.ldo_bf16 >= a.N / (a.ps_r * a.ps_r),
+                "gemm_tc: pixel-shuffle store needs a 16-bit-only conv epilogue with N %% r^2 == 0 and N / r^2 %% 8 == 0");
+  if (a.out_nchw)
+    GRL_REQUIRE(conv && p.epi == EPI_BIAS_ACT && a.nchw_r >= 1 && a.N_f32 % (a.nchw_r * a.nchw_r) == 0 &&
+                    a.N_f32 / (a.nchw_r * a.nchw_r) <= 4 && a.Hc > 0 && a.Wc > 0,
+                "gemm_tc: NCHW tail store needs a conv with <= 4 output channels");
   GRL_REQUIRE(p.taps == 1 || p.taps == 9, "gemm_tc: taps must be 1 or 9");
   // Epilogue mode.  fp32 staging (LayerNorm, fp32 output, residual) needs the whole output row in one tile, 16-byte
   // aligned fp32 rows and a tile that fits the staging area; anything else with an fp32 side takes the direct path.
@@ -535,6 +570,7 @@ int launch_gemm_tc(const GemmTcProblem& p, GemmTcArgs a, cudaStream_t st) {
     GRL_REQUIRE(ok || p.epi != EPI_LN, "gemm_tc: LayerNorm epilogue needs C %% 4 == 0 and C <= 188 (got %d)", cw);
     a.epi_mode = ok ? 1 : 2;
   }
+  if (a.out_nchw) a.epi_mode = 2;
   CUtensorMap tmA, tmB;
   int rc;
   dim3 grid;

@@ -43,6 +43,19 @@ inline int fail(int code, const char* fmt, ...) {
 
 constexpr int kMaxDevices = 64;  // per-device one-time kernel attributes (cudaFuncSetAttribute is per device)
 
+// SM count of the current device (cached per device): persistent kernels launch one CTA per SM
+inline int sm_count() {
+  static int n[kMaxDevices] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return 148;
+  if (n[dev] == 0) {
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+    n[dev] = v;
+  }
+  return n[dev];
+}
+
 inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 __device__ __forceinline__ float warp_sum(float v) {

@@ -62,6 +62,38 @@ __global__ void avgpool_bf16_kernel(const uint16_t* __restrict__ x, uint16_t* __
                  pack16(s[4] * inv, s[5] * inv, fmt), pack16(s[6] * inv, s[7] * inv, fmt));
 }
 
+// Network input: check_image_size (reflect pad to a multiple of pad_size, grl.py:479-489) + (x - mean) * img_range
+// (grl.py:510-511) + bchw -> channels-last + 16-bit operand pack, one pass.  One thread per padded pixel.
+struct HeadMean {
+  float m[4];
+};
+__global__ void head_pack_kernel(const float* __restrict__ x, int B, int Cin, int H, int W, int Hp, int Wp, HeadMean mean,
+                                 float range, int reflect, uint16_t* __restrict__ y16, int Cpad, float* __restrict__ y32,
+                                 int fmt) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)B * Hp * Wp) return;
+  const int xp = (int)(i % Wp);
+  const long long t = i / Wp;
+  const int yp = (int)(t % Hp), b = (int)(t / Hp);
+  int ys = yp, xs = xp;
+  bool inside = true;
+  if (reflect) {  // F.pad(..., "reflect") on the bottom / right: index 2 (n - 1) - p
+    if (ys >= H) ys = 2 * (H - 1) - ys;
+    if (xs >= W) xs = 2 * (W - 1) - xs;
+  } else {
+    inside = ys < H && xs < W;  // constant (zero) padding of the RAW image, normalised like every other pixel
+  }
+  float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int c = 0; c < Cin; ++c) {
+    const float raw = inside ? x[(((long long)b * Cin + c) * H + ys) * W + xs] : 0.f;
+    v[c] = (raw - mean.m[c]) * range;
+    if (y32) y32[i * Cin + c] = v[c];
+  }
+  uint4* dst = reinterpret_cast<uint4*>(y16 + i * Cpad);
+  dst[0] = make_uint4(pack16(v[0], v[1], fmt), pack16(v[2], v[3], fmt), pack16(v[4], v[5], fmt), pack16(v[6], v[7], fmt));
+  for (int c8 = 1; c8 < Cpad / 8; ++c8) dst[c8] = make_uint4(0u, 0u, 0u, 0u);
+}
+
 // Deterministic partial channel sums of bf16 features y (B, L, ld): partial (B, chunks, C) fp32.
 constexpr int kPoolRowsTc = 512;
 __global__ void channel_partial_bf16_kernel(const uint16_t* __restrict__ y, long long L, long long ld, int C, int fmt,
@@ -95,6 +127,19 @@ __global__ void slot_scale_kernel(const float* __restrict__ ls_w, const float* _
   }
 }
 
+int launch_head_pack(const float* x, int B, int Cin, int H, int W, int Hp, int Wp, const float* mean4, float range, void* y16,
+                     int Cpad, float* y32, int fmt, cudaStream_t st) {
+  GRL_REQUIRE(Cin >= 1 && Cin <= 4 && Cpad % 8 == 0 && Cpad >= 8 && Hp >= H && Wp >= W && H > 0 && W > 0,
+              "head_pack: bad shape (Cin %d, %dx%d -> %dx%d, Cpad %d)", Cin, H, W, Hp, Wp, Cpad);
+  const long long total = (long long)B * Hp * Wp;
+  if (total == 0) return GRL_OK;
+  HeadMean m;
+  for (int c = 0; c < 4; ++c) m.m[c] = mean4 ? mean4[c] : 0.f;
+  const int reflect = (Hp - H < H && Wp - W < W) ? 1 : 0;  // torch raises otherwise and the reference pads with zeros
+  head_pack_kernel<<<ceil_div(total, 256), 256, 0, st>>>(x, B, Cin, H, W, Hp, Wp, m, range, reflect, (uint16_t*)y16, Cpad, y32, fmt);
+  GRL_LAUNCH_CHECK("head_pack_kernel");
+  return GRL_OK;
+}
 int launch_pack_bf16(const float* x, long long ldx, void* y, long long M, int C, int Cpad, int fmt, cudaStream_t st) {
   GRL_REQUIRE(Cpad % 8 == 0 && Cpad >= C, "pack_bf16: bad padding %d for %d channels", Cpad, C);
   if (M == 0) return GRL_OK;

@@ -15,7 +15,7 @@ struct GemmTcArgs {
   int fmt;  // operand / 16-bit activation format: 0 = fp16, 1 = bf16
   // filled by launch_gemm_tc
   long long M;
-  int nk, taps, n_tiles;
+  int nk, taps, n_tiles, total_tiles;
   int H, W, tiles_x, tiles_y;
   int epi_mode;  // 0 = 16-bit staging, 1 = fp32 staging, 2 = direct
   // epilogue
@@ -41,6 +41,13 @@ struct GemmTcArgs {
   long long ld_caby;
   const float* cab_gate;
   long long L;
+  // head / tail fusion (conv only)
+  int ps_r;         // > 0: PixelShuffle(ps_r) folded into the 16-bit store: column n' = q * (N / r^2) + c goes to pixel
+                    // (y r + q / r, x r + q % r), channel c of a (B, H r, W r, ldo) tensor (weights packed in that order)
+  float* out_nchw;  // direct epilogue: final image planes (B, N_f32 / nchw_r^2, Hc, Wc) = value * post_scale + post_shift[c],
+  int nchw_r;       // PixelShuffle(nchw_r) (torch channel order c r^2 + dy r + dx) and the crop to (Hc, Wc) folded into the store
+  int Hc, Wc;
+  float post_scale, post_shift[4];
 };
 
 struct GemmTcProblem {
@@ -88,12 +95,17 @@ int attn_tma_box_tokens(const GrlGrid& g);
 // persistent warp-specialised kernel (attn2.cu): P and O in TMEM, NWG query tiles share each K / V tile; returns +1 when the
 // geometry has no TMA box form
 int launch_attn2(const AttnTcArgs& a, cudaStream_t st);
+int attn2_debug(int* out8);  // {timed_out, wait site, block, warp, parity, barrier smem offset, 0, 0} of the first timed-out wait; clears it
 
 }  // namespace tc
 }  // namespace grl
 
 namespace grl {
 namespace tc {
+// reflect-pad (or zero-pad when the pad exceeds the image, as grl.py:485-488 falls back) + (x - mean) * range + NCHW -> NHWC +
+// 16-bit pack of the network input: x (B, Cin, H, W) fp32 -> y16 (B, Hp, Wp, Cpad) and, optionally, y32 (B, Hp, Wp, Cin)
+int launch_head_pack(const float* x, int B, int Cin, int H, int W, int Hp, int Wp, const float* mean4, float range, void* y16,
+                     int Cpad, float* y32, int fmt, cudaStream_t st);
 int launch_pack_bf16(const float* x, long long ldx, void* y, long long M, int C, int Cpad, int fmt, cudaStream_t st);
 int launch_unpack_bf16(const void* x, long long ldx, int x_off, float* y, long long ldy, long long M, int C, int fmt,
                        cudaStream_t st);

@@ -740,26 +740,42 @@ class GRL(nn.Module):
         return t.view(B, H, W, C)
 
     @torch.no_grad()
-    def _forward_bf16(self, x, H, W):
-        """Head / tail on the tensor-core conv kernels (grl.py:506-551); x is padded, normalised fp32 NCHW."""
+    def _forward_bf16(self, x):
+        """grl.py:506-551 on the tensor-core kernels; x is the RAW (B, Cin, H, W) fp32 input.  Head: one kernel does
+        check_image_size + (x - mean) * img_range + bchw -> bhwc + operand pack; tail: the last conv's epilogue writes
+        x / img_range + mean, cropped, as bchw planes; PixelShuffle is a store-address pattern of the conv before it."""
         from . import tc
 
         dev = x.device
         fmt = tc.FMT[self.precision]
-        B, Cin, Hp, Wp = x.shape
+        B, Cin, H, W = x.shape
+        Hp = (H + self.pad_size - 1) // self.pad_size * self.pad_size
+        Wp = (W + self.pad_size - 1) // self.pad_size * self.pad_size
         C = self.embed_dim
         cpad = tc.round_up(C, 64)
-        xc = x.permute(0, 2, 3, 1).contiguous()
-        x16 = tc.pack_rows(xc, 64, fmt)
+        s = self.upscale
+        need_res = self.upsampler not in ("pixelshuffle", "pixelshuffledirect", "nearest+conv") and self.in_channels == self.out_channels
+        x16, xc32 = tc.head_pack(x, Hp, Wp, self.mean, self.img_range, 64, fmt, want_f32=need_res)
+        mean = [float(v) for v in self.mean.flatten().tolist()]
+        shift = mean if len(mean) > 1 else mean * 4
 
-        def conv(name, module, inp16, cin_pad, *, act=K.ACT_NONE, slope=0.0, res=None, want_f32=False, want16=True):
-            plan = tc.conv_plan(self, name, module, cin_pad, fmt)
+        def conv(name, module, inp16, cin_pad, *, act=K.ACT_NONE, slope=0.0, res=None, want_f32=False, want16=True, ps_r=0,
+                 final_r=0):
+            plan = tc.conv_plan(self, name, module, cin_pad, fmt, ps_r)
             b, h, w, _ = inp16.shape
-            o16 = torch.empty(b, h, w, plan.npad, device=dev, dtype=tc.DTYPE[fmt]) if want16 else None
-            o32 = torch.empty(b, h, w, plan.cout, device=dev, dtype=torch.float32) if want_f32 else None
-            tc.conv3x3(inp16, plan.w, plan.b, cin_pad, plan.npad, n_store=plan.npad, n_real=plan.cout, act=act, slope=slope,
-                       out_bf16=o16, out_f32=o32, res_f32=res)
-            return o16, o32
+            tail, o16, o32 = {}, None, None
+            if final_r:  # network output: (B, C_out, H s, W s) planes straight from the epilogue
+                tail = dict(out_nchw=torch.empty(B, self.out_channels, H * s, W * s, device=dev, dtype=torch.float32),
+                            nchw_r=final_r, post_scale=1.0 / self.img_range, post_shift=shift)
+            elif ps_r:
+                o16 = torch.empty(b, h * ps_r, w * ps_r, plan.cout // (ps_r * ps_r), device=dev, dtype=tc.DTYPE[fmt])
+                tail = dict(ps_r=ps_r)
+            else:
+                o16 = torch.empty(b, h, w, plan.npad, device=dev, dtype=tc.DTYPE[fmt]) if want16 else None
+                o32 = torch.empty(b, h, w, plan.cout, device=dev, dtype=torch.float32) if want_f32 else None
+            tc.conv3x3(inp16, plan.w, plan.b, cin_pad, plan.npad, n_store=plan.cout if ps_r else plan.npad, n_real=plan.cout,
+                       act=act, slope=slope, out_bf16=o16, out_f32=o32, res_f32=res, **tail)
+            return (tail["out_nchw"], None) if final_r else (o16, o32)
 
         f16, f32 = conv("conv_first", self.conv_first, x16, 64, want_f32=True)
         feat = f32.view(B, Hp * Wp, C)
@@ -769,32 +785,26 @@ class GRL(nn.Module):
             t = layer(t, (Hp, Wp), tim)
         t = K.ln_residual(None, t, self.norm_end.weight, self.norm_end.bias, self.norm_end.eps)
         t16 = tc.pack_rows(t, cpad, fmt).view(B, Hp, Wp, cpad)
-        last_f32 = self.upsampler not in ("pixelshuffle", "nearest+conv")
-        body16, body32 = conv("conv_after_body", self.conv_after_body, t16, cpad, res=f32, want_f32=last_f32)
+        body16, _ = conv("conv_after_body", self.conv_after_body, t16, cpad, res=f32)
         if self.upsampler == "pixelshuffle":
             u16, _ = conv("conv_before_upsample", self.conv_before_upsample[0], body16, cpad, act=K.ACT_LEAKY, slope=0.01)
-            for i, m in enumerate(self.upsample.up):
-                if isinstance(m, nn.Conv2d):
-                    u16, _ = conv(f"upsample.up.{i}", m, u16, u16.shape[-1])
-                else:
-                    u16 = pixel_shuffle_cl(u16[..., : u16.shape[-1]], m.upscale_factor).contiguous()
-            _, y = conv("conv_last", self.conv_last, u16, u16.shape[-1], want_f32=True, want16=False)
+            mods = list(self.upsample.up)
+            for i, m in enumerate(mods):
+                if isinstance(m, nn.Conv2d):  # always followed by its PixelShuffle (upsample.py:6-30)
+                    u16, _ = conv(f"upsample.up.{i}", m, u16, u16.shape[-1], ps_r=mods[i + 1].upscale_factor)
+            y, _ = conv("conv_last", self.conv_last, u16, u16.shape[-1], final_r=1)
         elif self.upsampler == "pixelshuffledirect":
-            m = self.upsample.up[0]
-            _, y = conv("upsample.up.0", m, body16, cpad, want_f32=True, want16=False)
-            y = pixel_shuffle_cl(y, self.upsample.up[1].upscale_factor)
+            y, _ = conv("upsample.up.0", self.upsample.up[0], body16, cpad, final_r=self.upsample.up[1].upscale_factor)
         elif self.upsampler == "nearest+conv":
             u16, _ = conv("conv_before_upsample", self.conv_before_upsample[0], body16, cpad, act=K.ACT_LEAKY, slope=0.01)
             up = lambda v: v.repeat_interleave(2, dim=1).repeat_interleave(2, dim=2).contiguous()
             u16, _ = conv("conv_up1", self.conv_up1, up(u16), u16.shape[-1], act=K.ACT_LEAKY, slope=0.2)
             u16, _ = conv("conv_up2", self.conv_up2, up(u16), u16.shape[-1], act=K.ACT_LEAKY, slope=0.2)
             u16, _ = conv("conv_hr", self.conv_hr, u16, u16.shape[-1], act=K.ACT_LEAKY, slope=0.2)
-            _, y = conv("conv_last", self.conv_last, u16, u16.shape[-1], want_f32=True, want16=False)
+            y, _ = conv("conv_last", self.conv_last, u16, u16.shape[-1], final_r=1)
         else:
-            res = xc if self.in_channels == self.out_channels else None
-            _, y = conv("conv_last", self.conv_last, body16, cpad, res=res, want_f32=True, want16=False)
-        y = y.permute(0, 3, 1, 2) / self.img_range + self.mean
-        return y[:, :, : H * self.upscale, : W * self.upscale].contiguous()
+            y, _ = conv("conv_last", self.conv_last, body16, cpad, res=xc32, final_r=1)
+        return y
 
     def forward_features(self, x):
         """(B, C, H, W) -> (B, C, H, W) like the reference."""
@@ -805,11 +815,11 @@ class GRL(nn.Module):
     def forward(self, x):
         K.capi.require_device(x)
         H, W = x.shape[2:]
+        if self.precision != "fp32":
+            return self._forward_bf16(x.float().contiguous()).to(x.dtype)
         x = self.check_image_size(x)
         self.mean = self.mean.type_as(x)
         x = ((x - self.mean) * self.img_range).float()
-        if self.precision != "fp32":
-            return self._forward_bf16(x, H, W)
         xc = x.permute(0, 2, 3, 1).contiguous()  # channels-last from here on
         first = self._conv("conv_first", self.conv_first, xc)
         body = self._conv("conv_after_body", self.conv_after_body, self._features_cl(first), res=first)

@@ -46,6 +46,20 @@ def _h16(*shape, device, fmt, zero=False):
     return (torch.zeros if zero else torch.empty)(*shape, device=device, dtype=DTYPE[fmt])
 
 
+def head_pack(x, hp, wp, mean, img_range, cpad=64, fmt=0, want_f32=False):
+    """Network input (B, Cin, H, W) fp32 -> 16-bit channels-last (B, hp, wp, cpad) [+ fp32 (B, hp, wp, Cin)]: reflect pad,
+    (x - mean) * img_range, layout change and operand pack in one kernel (grl_tc_head_pack)."""
+    B, Cin, H, W = x.shape
+    y16 = _h16(B, hp, wp, cpad, device=x.device, fmt=fmt)
+    y32 = torch.empty(B, hp, wp, Cin, device=x.device, dtype=torch.float32) if want_f32 else None
+    m = [float(v) for v in mean.flatten().tolist()]
+    m = (m * 4)[:4] if len(m) == 1 else (m + [0.0] * 4)[:4]
+    arr = (ctypes.c_float * 4)(*m)
+    capi.check(capi.lib().grl_tc_head_pack(capi.ptr(x), B, Cin, H, W, hp, wp, arr, float(img_range), capi.ptr(y16), cpad,
+                                           capi.ptr(y32), fmt, capi.stream()))
+    return y16, y32
+
+
 def pack_rows(x, cpad, fmt=0):
     """fp32 (..., C) contiguous -> 16-bit (..., cpad), zero padded."""
     C = x.shape[-1]
@@ -82,21 +96,27 @@ def _pad_vector(b, npad, row_map=None):
     return out
 
 
-def pack_conv(conv, cin_pad, npad, fmt=0):
-    """nn.Conv2d(3x3) weight (Cout, Cin, 3, 3) -> 16-bit (npad, 9*cin_pad), k = (ky*3+kx)*cin_pad + c; bias fp32 (npad)."""
+def pack_conv(conv, cin_pad, npad, fmt=0, ps_r=0):
+    """nn.Conv2d(3x3) weight (Cout, Cin, 3, 3) -> 16-bit (npad, 9*cin_pad), k = (ky*3+kx)*cin_pad + c; bias fp32 (npad).
+    ps_r > 0: the conv feeds nn.PixelShuffle(ps_r): output channel c*r^2 + q (torch order) is stored at row q*(Cout/r^2) + c,
+    so the channels of one shuffled pixel are consecutive output columns (grl_tc_gemm's ps_r store)."""
     w = conv.weight.detach().float()
     co, ci = w.shape[:2]
+    rows = torch.arange(co, device=w.device)
+    if ps_r > 0:
+        cq = co // (ps_r * ps_r)
+        rows = (rows % (ps_r * ps_r)) * cq + rows // (ps_r * ps_r)
     out = torch.zeros(npad, 9, cin_pad, device=w.device, dtype=torch.float32)
-    out[:co, :, :ci] = w.permute(0, 2, 3, 1).reshape(co, 9, ci)
+    out[rows, :, :ci] = w.permute(0, 2, 3, 1).reshape(co, 9, ci)
     bias = torch.zeros(npad, device=w.device, dtype=torch.float32)
     if conv.bias is not None:
-        bias[:co] = conv.bias.detach().float()
+        bias[rows] = conv.bias.detach().float()
     return out.reshape(npad, 9 * cin_pad).to(DTYPE[fmt]).contiguous(), bias
 
 
 def gemm(x16, w16, bias, *, M=0, image=None, kpad, npad, taps=1, epi=EPI_BIAS_ACT, n_store=0, n_real=0, out_bf16=None,
          out_f32=None, res_f32=None, act=K.ACT_NONE, slope=0.0, slot_scale=None, C=0, gamma=None, beta=None, eps=1e-5,
-         res_scale=1.0, cab_y=None, cab_gate=None, L=1):
+         res_scale=1.0, cab_y=None, cab_gate=None, L=1, ps_r=0, out_nchw=None, nchw_r=1, post_scale=1.0, post_shift=None):
     p = capi.GrlTcGemm()
     if x16.dtype != w16.dtype:
         raise RuntimeError("grl_b200: activation / weight operand formats differ")
@@ -123,6 +143,12 @@ def gemm(x16, w16, bias, *, M=0, image=None, kpad, npad, taps=1, epi=EPI_BIAS_AC
     if cab_y is not None:
         p.cab_y, p.ld_caby, p.cab_gate = cab_y.data_ptr(), cab_y.shape[-1], cab_gate.data_ptr()
     p.L = L
+    p.ps_r = ps_r
+    if out_nchw is not None:  # (B, C_out, Hc, Wc) fp32 planes: denormalise + crop + bhwc -> bchw folded into the store
+        p.out_nchw, p.nchw_r, p.Hc, p.Wc = out_nchw.data_ptr(), nchw_r, out_nchw.shape[2], out_nchw.shape[3]
+        p.post_scale = post_scale
+        for i in range(4):
+            p.post_shift[i] = float(post_shift[i]) if post_shift is not None and i < len(post_shift) else 0.0
     capi.check(capi.lib().grl_tc_gemm(ctypes.byref(p), capi.stream()))
 
 
@@ -169,11 +195,11 @@ def bias_table_log2(transform, table):
 
 
 def conv3x3(x16, wpack, bias, cin_pad, npad, *, n_store, n_real=0, act=K.ACT_NONE, slope=0.0, out_bf16=None,
-            out_f32=None, res_f32=None):
-    """x16 bf16 (B, H, W, cin_pad) channels-last."""
+            out_f32=None, res_f32=None, **tail):
+    """x16 bf16 (B, H, W, cin_pad) channels-last.  tail: ps_r / out_nchw / nchw_r / post_scale / post_shift (head-tail fusion)."""
     B, H, W, _ = x16.shape
     gemm(x16, wpack, bias, image=(B, H, W), kpad=cin_pad, npad=npad, taps=9, epi=EPI_BIAS_ACT, n_store=n_store,
-         n_real=n_real, out_bf16=out_bf16, out_f32=out_f32, res_f32=res_f32, act=act, slope=slope)
+         n_real=n_real, out_bf16=out_bf16, out_f32=out_f32, res_f32=res_f32, act=act, slope=slope, **tail)
 
 
 def _version_key(module):
@@ -346,18 +372,18 @@ def block_plan(blk, fmt):
 class ConvPlan:
     """One packed 3x3 conv (stage conv / head convs)."""
 
-    def __init__(self, conv, cin_pad, fmt):
-        self.key = (_version_key(conv), fmt)
+    def __init__(self, conv, cin_pad, fmt, ps_r=0):
+        self.key = (_version_key(conv), fmt, ps_r)
         self.cout = conv.weight.shape[0]
         self.cin_pad = cin_pad
         self.npad = round_up(self.cout, 64)
-        self.w, self.b = pack_conv(conv, cin_pad, self.npad, fmt)
+        self.w, self.b = pack_conv(conv, cin_pad, self.npad, fmt, ps_r)
 
 
-def conv_plan(owner, name, conv, cin_pad, fmt):
+def conv_plan(owner, name, conv, cin_pad, fmt, ps_r=0):
     cache = owner.__dict__.setdefault("_tc_convs", {})
     plan = cache.get(name)
-    if plan is None or plan.key != (_version_key(conv), fmt) or plan.cin_pad != cin_pad:
-        plan = ConvPlan(conv, cin_pad, fmt)
+    if plan is None or plan.key != (_version_key(conv), fmt, ps_r) or plan.cin_pad != cin_pad:
+        plan = ConvPlan(conv, cin_pad, fmt, ps_r)
         cache[name] = plan
     return plan

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define GRL_B200_ABI_VERSION 1
+#define GRL_B200_ABI_VERSION 2
 
 typedef enum {
   GRL_OK = 0,
@@ -146,6 +146,12 @@ int grl_tc_bias_table4(const float* table, int rows, const float* w1, const floa
 /* fp32 (M, C) rows of pitch ldx -> 16-bit (M, Cpad) zero-padded; and back (16-bit rows of pitch ldx, column offset). */
 int grl_tc_pack16(const float* x, int64_t ldx, void* y16, int64_t M, int C, int Cpad, int fmt, void* stream);
 int grl_tc_unpack16(const void* x16, int64_t ldx, int x_off, float* y, int64_t ldy, int64_t M, int C, int fmt, void* stream);
+/* Network input in one pass: check_image_size (reflect pad on the bottom / right up to (Hp, Wp); zero pad when the pad
+ * exceeds the image, as grl.py:485-488 falls back) + (x - mean) * img_range (grl.py:510-511) + bchw -> channels-last +
+ * 16-bit pack.  x (B, Cin <= 4, H, W) fp32 -> y16 (B, Hp, Wp, Cpad), zero in [Cin, Cpad); y32 (may be NULL): the fp32
+ * channels-last copy (B, Hp, Wp, Cin) the no-upsampler heads add back (grl.py:540-547).  mean4: 4 HOST floats. */
+int grl_tc_head_pack(const float* x, int B, int Cin, int H, int W, int Hp, int Wp, const float* mean4, float range, void* y16,
+                     int Cpad, float* y32, int fmt, void* stream);
 /* AvgPool2d(df) on 16-bit channels-last data (AnchorLinear.pooling, mixed_attn_block.py:725). */
 int grl_tc_avgpool16(const void* x16, void* y16, int B, int H, int W, int Cpad, int df, int fmt, void* stream);
 /* Per-slot multipliers of the packed qkv layout [win q|k|v][stripe q|k|v] x heads: exp(min(logit_scale, ln100))*log2(e)
@@ -193,6 +199,17 @@ typedef struct {
   int64_t ld_caby;
   const float* cab_gate;
   int64_t L;
+  /* head / tail fusion (taps == 9 only; zero = off).
+   * ps_r > 0: PixelShuffle(ps_r) folded into the 16-bit store (models/common/upsample.py:6-30): w rows must be packed so
+   *   that output column n' = q * (n_store / r^2) + c holds torch channel c * r^2 + q; out_bf16 is (B, H r, W r, ldo_bf16).
+   * out_nchw: final image planes (B, n_real / nchw_r^2, Hc, Wc) fp32 = value * post_scale + post_shift[c]: x / img_range +
+   *   mean, the crop to (Hc, Wc) and bhwc -> bchw (grl.py:549-551) folded into the store; nchw_r > 1 additionally folds
+   *   UpsampleOneStep's PixelShuffle (upsample.py:33-50, torch channel order). */
+  int32_t ps_r;
+  float* out_nchw;
+  int32_t nchw_r, Hc, Wc;
+  float post_scale;
+  float post_shift[4];
 } GrlTcGemm;
 int grl_tc_gemm(const GrlTcGemm* p, void* stream);
 
@@ -232,6 +249,10 @@ int grl_tc_attn(const GrlTcAttn* p, void* stream);
  * run variant 0).  Initial value: environment variable GRL_ATTN_SPLIT
  * (unset = 0).  Returns the previous value; a value outside {0..4} only queries.  Same results contract as variant 0. */
 int grl_tc_attn_variant(int variant);
+/* Diagnosis of the persistent attention kernel's pipeline: out8 = {1 if an mbarrier wait timed out (~0.5 s) since the last
+ * call, wait site id (csrc/attn2.cu), block, warp, parity, barrier shared-memory offset, 0, 0}; reading clears it.  A timed-out
+ * launch finishes with undefined results instead of hanging the GPU. */
+int grl_tc_attn2_debug(int* out8);
 
 /* ---- validation metric -------------------------------------------------- */
 /* Per-image PSNR of the reference's validation step in one fused pass: tensor_round (utils/utils_image.py:30-33) of

@@ -15,7 +15,7 @@ def test_library_exports_every_header_symbol(pkg):
     for n in names:
         assert hasattr(handle, n), f"{n} declared in include/grl_b200.h but not exported"
     assert set(names) == set(capi._SIGNATURES), "ctypes signatures out of sync with the header"
-    assert capi.lib().grl_abi_version() == 1
+    assert capi.lib().grl_abi_version() == capi.ABI_VERSION
 
 
 def test_library_is_sm100a_native(pkg):

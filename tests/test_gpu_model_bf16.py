@@ -87,3 +87,38 @@ def test_bf16_fp32_switch_and_batch_invariance(pkg, oracle, device):
     p = (-10 * torch.log10(((y[:1] - y32) ** 2).mean())).item()
     print(f"base sr 256: PSNR(fp16 path, fp32 path) = {p:.1f} dB, max-abs {(y[:1] - y32).abs().max().item():.3e}")
     assert p >= 25.0
+
+
+@pytest.mark.parametrize("name", ["cfg1_tiny_x2_64", "micro_cab_x2", "micro_pad_dn", "micro_groups", "micro_odd_d", "micro_gray"])
+def test_head_tail_fusion_all_heads(pkg, oracle, cases, device, name):
+    """The fused head (reflect / zero pad + normalise + layout + pack in one kernel) and tails (PixelShuffle as a store
+    pattern, x / range + mean + crop + bchw in the last conv's epilogue) of the tensor-core path against the fp32 path
+    (torch-op head / tail, exact-parity kernels) for every head type: pixelshuffle, pixelshuffledirect (x3),
+    nearest+conv, no upsampler with the input residual, 1-channel input, inputs that need padding."""
+    c = cases[name]
+    cfg = c["cfg"]
+    sd = oracle.synth_state_dict(cfg, seed=0, style="init")
+    m = pkg.GRL(**cfg)
+    m.load_state_dict(sd, strict=False)
+    m = m.to(device).eval()
+    if m.set_precision("auto") == "fp32":
+        pytest.skip("architecture outside the tensor-core path")
+    x = oracle.synth_input((c["batch"], cfg["in_channels"], *c["hw"]), seed=1234, noise_sigma=c["sigma"]).to(device)
+    y16 = m(x)
+    m.set_precision("fp32")
+    y32 = m(x)
+    assert y16.shape == y32.shape and y16.is_contiguous() and torch.isfinite(y16).all()
+    p = (-10 * torch.log10(((y16 - y32) ** 2).mean())).item()
+    print(f"{name}: fp16 path vs fp32 path PSNR {p:.1f} dB, max-abs {(y16 - y32).abs().max().item():.3e}")
+    assert p >= 50.0
+    # odd sizes: crop + pad of a non-multiple input (configs with stripe_groups need square padded inputs: the reference
+    # itself crashes otherwise, SURVEY.md Appendix D.2)
+    if any(g is not None for g in cfg["stripe_groups"]):
+        return
+    xo = x[..., : x.shape[-2] - 3, : x.shape[-1] - 5].contiguous()
+    m.set_precision("auto")
+    a = m(xo)
+    m.set_precision("fp32")
+    b = m(xo)
+    assert a.shape == b.shape
+    assert (-10 * torch.log10(((a - b) ** 2).mean())).item() >= 50.0

@@ -12,15 +12,12 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 PKG = os.path.join(ROOT, "grl-image-restoration_b200")
 LIB = os.path.join(PKG, "libgrl_b200.so")
 AB = os.path.join(ROOT, "ab")
+STUB = "-DGRL_A2_DIAG_NOBIAS -DGRL_A2_DIAG_NOEXP -DGRL_A2_DIAG_NOLDTM -DGRL_A2_DIAG_NOSTTM -DGRL_A2_DIAG_NOMAX"
 VARIANTS = {
     "base": "",
-    "nobias": "-DGRL_A2_DIAG_NOBIAS",
-    "noexp": "-DGRL_A2_DIAG_NOEXP",
-    "noldtm": "-DGRL_A2_DIAG_NOLDTM",
-    "nosttm": "-DGRL_A2_DIAG_NOSTTM",
-    "nomax": "-DGRL_A2_DIAG_NOMAX",
-    "noexp_nobias": "-DGRL_A2_DIAG_NOEXP -DGRL_A2_DIAG_NOBIAS",
-    "stub": "-DGRL_A2_DIAG_NOBIAS -DGRL_A2_DIAG_NOEXP -DGRL_A2_DIAG_NOLDTM -DGRL_A2_DIAG_NOSTTM -DGRL_A2_DIAG_NOMAX",
+    "bgsleep": "-DGRL_A2_BG_SLEEP",
+    "stub": STUB,
+    "stub_bgsleep": STUB + " -DGRL_A2_BG_SLEEP",
 }
 
 

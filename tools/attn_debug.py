@@ -130,6 +130,11 @@ for variant in [int(v) for v in a.variants.split(",")]:
     print(f"=== variant {variant}  (B={B}, {H}x{W}, heads {heads}, logit scale {a.scale})")
     m1, x1 = run_all(q16, a16, B)
     torch.cuda.synchronize()
+    import ctypes as _ct
+    _dbg = (_ct.c_int * 8)()
+    capi.lib().grl_tc_attn2_debug(_dbg)
+    if _dbg[0]:
+        print("  !! attn2 wait timed out: site", _dbg[1], "block", _dbg[2], "warp", _dbg[3], "parity", _dbg[4], "bar offset", hex(_dbg[5]))
     m2, x2 = run_all(q16, a16, B)
     torch.cuda.synchronize()
     stats("window  vs fp32", m1[:, :heads * 32].float()[..., :], ref_w)
