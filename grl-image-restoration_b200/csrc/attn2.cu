@@ -227,6 +227,16 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) {
   return d;
 }
 
+// MMA issuer warps per CTA: one for every warpgroup (GRL_A2_MULTI_ISSUER, A/B build) or a single one (default)
+template <int NWG>
+__host__ __device__ constexpr int kIssuers2() {
+#ifdef GRL_A2_MULTI_ISSUER
+  return NWG;
+#else
+  return 1;
+#endif
+}
+
 struct Item {
   int qg, h, bw, b, wr, wc, nact;
 };
@@ -246,7 +256,7 @@ struct Ring {
 };
 
 template <int NWG, int KW, int VAR, bool BS>
-__global__ void __launch_bounds__(NWG * 128 + 32 + NWG * 32, 1)
+__global__ void __launch_bounds__(NWG * 128 + 32 + kIssuers2<NWG>() * 32, 1)
 attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
              const __grid_constant__ CUtensorMap tmV, const AttnTcArgs a, const A2Geom tg) {
   extern __shared__ uint8_t smem_raw[];
@@ -296,7 +306,7 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
     }
     for (int s = 0; s < NS; ++s) {
       mbar_init(&kv_full[s], 1);
-      mbar_init(&kv_empty[s], NWG);
+      mbar_init(&kv_empty[s], kIssuers2<NWG>());
       mbar_init(&meta_full[s], 1);
     }
     mbar_init(bias_full, 1);
@@ -416,6 +426,7 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
           __syncwarp();
         }
       }
+#ifdef GRL_A2_MULTI_ISSUER
     } else if (warp <= 4 * NWG + NWG) {
       // =============================================================== MMA issuers: one warp (one thread) per warpgroup.
       // Each issuer owns the MMAs of ONE warpgroup (the ordering the S / P aliasing needs is within a warpgroup); all of
@@ -493,6 +504,94 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
       // every commit has arrived before the CTA's shared memory goes away (kv_empty needs all NWG issuers)
       if (kv_it > 0) mbar_wait_bg(&kv_empty[rl.st], rl.ph, 8);
     }
+#else
+    } else if (warp == 4 * NWG + 1) {
+      // =============================================================== MMA issuer: ONE warp (one thread) serves every
+      // warpgroup in turn (measured ~10 % faster end to end than one issuer warp per warpgroup: fewer warps polling next
+      // to the softmax warps).  After EVERY tile t of warpgroup g it commits to bar_s[g][t & 1] ("P V(t) done and, if it
+      // exists, S(t+2) ready"); the softmax warps consume these completions strictly in order per buffer, so every parity
+      // wait is exact; the two completions past the last tile are the "O final" signal.
+      const uint32_t idesc_qk = umma_idesc(kQT, KT, fmt, 0, 0);
+      const uint32_t idesc_pv = umma_idesc(kQT, kDP, fmt, 0, 1);
+      // descriptors: only the 14-bit start-address field (16-byte units) changes between uses
+      const uint64_t q_desc0 = umma_desc(smem_u32(Qs), 16, 512, SWZ_64B);
+      const uint64_t k_desc0 = umma_desc(smem_u32(Ks), 16, 512, SWZ_64B);
+      const uint64_t v_desc0 = umma_desc(smem_u32(Vs), 16, 512, SWZ_64B);
+      uint32_t kv_it = 0, q_cnt[NWG], p_cnt[NWG][2], d_cnt[NWG];
+#pragma unroll
+      for (int g = 0; g < NWG; ++g) q_cnt[g] = 0, p_cnt[g][0] = 0, p_cnt[g][1] = 0, d_cnt[g] = 0;
+      Ring r0 = {0, 0}, r2 = {0, 0}, rl = {0, 0};  // tile t, tile t + 2, last tile handled
+      r2.adv(NS);
+      r2.adv(NS);
+      auto issue_qk = [&](int g, int st, int buf, bool last) {  // lane 0
+        const uint64_t qd = q_desc0 + (uint64_t)(g * (S::Q_BYTES >> 4));
+        const uint64_t kd = k_desc0 + (uint64_t)(st * (S::KV_BYTES >> 4));
+        A2_QK(umma_ss(tmem + g * kColsPerWg + buf * 64, qd, kd, idesc_qk, false));
+        A2_QK(umma_ss(tmem + g * kColsPerWg + buf * 64, qd + 2, kd + 2, idesc_qk, true));
+        if (last) umma_commit(&q_empty[g]);
+      };
+      for (int item = my_c; item < tg.per_head; item += cph) {
+        const Item it = decode(item);
+        // prologue: S_g(0) and S_g(1)
+        Ring rq = r0;  // ring position of tile t0
+        for (int t0 = 0; t0 < 2 && t0 < ntiles; ++t0, rq.adv(NS)) {
+          const int st = rq.st;
+          mbar_wait_bg(&kv_full[st], rq.ph, 4);
+#pragma unroll
+          for (int g = 0; g < NWG; ++g) {
+            if (g < it.nact) {
+              if (t0 == 0) {
+                mbar_wait_bg(&q_full[g], q_cnt[g] & 1, 3);
+                ++q_cnt[g];
+              }
+              if (lane == 0) {
+                tcgen05_fence_after();
+                issue_qk(g, st, t0, t0 + 1 == ntiles);
+                umma_commit(&bar_s[2 * g + t0]);
+                if (ntiles == 1) umma_commit(&bar_s[2 * g + 1]);  // keep both buffers' counts in step
+              }
+              __syncwarp();
+            }
+          }
+        }
+        for (int t = 0; t < ntiles; ++t, ++kv_it, rl = r0, r0.adv(NS), r2.adv(NS)) {
+          const int st = r0.st, st2 = r2.st;
+          if (t + 2 < ntiles) mbar_wait_bg(&kv_full[st2], r2.ph, 5);
+#pragma unroll
+          for (int g = 0; g < NWG; ++g) {
+            if (g < it.nact) {
+              // (per S buffer: the softmax warps run up to two tiles ahead of this thread, and an mbarrier that completes
+              // twice before its waiter has looked is indistinguishable from one that has not completed)
+              mbar_wait_bg(&p_full[2 * g + (t & 1)], p_cnt[g][t & 1] & 1, 6);
+              ++p_cnt[g][t & 1];
+              if (lane == 0) {
+                tcgen05_fence_after();
+                const uint64_t vd = v_desc0 + (uint64_t)(st * (S::KV_BYTES >> 4));
+                const uint32_t wg_ta = tmem + g * kColsPerWg;
+                const uint32_t p_ta = wg_ta + (t & 1) * 64;
+#pragma unroll
+                for (int k = 0; k < KT / 16; ++k) A2_PV(umma_ts(wg_ta + 128, p_ta + k * 8, vd + (uint64_t)(k * 64), idesc_pv, (t | k) != 0));
+                if (t + 2 < ntiles) issue_qk(g, st2, t & 1, t + 3 == ntiles);
+                umma_commit(&bar_s[2 * g + (t & 1)]);  // P V(t) done (+ S(t+2) ready)
+              }
+              __syncwarp();
+            }
+          }
+          if (lane == 0) A2_KVCOMMIT(&kv_empty[st]);  // every MMA that reads stage st has been issued
+          __syncwarp();
+        }
+#pragma unroll
+        for (int g = 0; g < NWG; ++g) {
+          if (g < it.nact) {  // the warpgroup has consumed this item's closing completions of bar_s (see its epilogue)
+            mbar_wait_bg(&item_done[g], d_cnt[g] & 1, 7);
+            ++d_cnt[g];
+          }
+        }
+      }
+      // every commit has arrived before the CTA's shared memory goes away
+      if (kv_it > 0) mbar_wait_bg(&kv_empty[rl.st], rl.ph, 8);
+    }
+#endif
   } else {
     // =============================================================== softmax warpgroups: thread = query row
     const int row = tid & 127;
@@ -751,7 +850,7 @@ int launch2_var(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap&
   tg.stages = std::min(kMaxStages2, (kMaxSmem - A2Smem<NWG>::FIXED - bias_bytes) / (2 * A2Smem<NWG>::KV_BYTES));
   GRL_REQUIRE(tg.stages >= 4, "attn2: no room for the K / V ring");
   const int smem = A2Smem<NWG>::total(tg.stages, bias_bytes);
-  kern<<<grid, NWG * 128 + 32 + NWG * 32, smem, st>>>(tq, tk, tv, a, tg);
+  kern<<<grid, NWG * 128 + 32 + kIssuers2<NWG>() * 32, smem, st>>>(tq, tk, tv, a, tg);
   GRL_LAUNCH_CHECK("attn2_kernel");
   return GRL_OK;
 }
@@ -763,7 +862,7 @@ int launch2_bs(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& 
   // ~7.5 tag lookups (the 128-byte runs of the four copies are not line aligned) -- the L1 data pipe was the busiest unit
   static const bool off = [] { const char* e = getenv("GRL_ATTN2_NO_SMEM_BIAS"); return e && e[0] == '1'; }();
   // ... as long as the table leaves room for a ring deep enough to cover the TMA latency (>= min_ring stages)
-  static const int min_ring = [] { const char* e = getenv("GRL_ATTN2_MIN_RING"); return e ? atoi(e) : 8; }();
+  static const int min_ring = [] { const char* e = getenv("GRL_ATTN2_MIN_RING"); return e ? atoi(e) : 6; }();
   if (KW > 0 && !off && A2Smem<NWG>::total(min_ring, 16 * a.rows_pad) <= kMaxSmem)
     return launch2_var<NWG, KW, VAR, (KW > 0)>(tq, tk, tv, a, tg, st);
   return launch2_var<NWG, KW, VAR, false>(tq, tk, tv, a, tg, st);
@@ -804,6 +903,7 @@ int attn2_debug_read(int* out8) {
 }  // namespace
 
 int attn2_debug(int* out8) { return attn2_debug_read(out8); }
+int attn_tma_box_tokens(const GrlGrid& g) { return box_tokens2(g); }
 
 // Returns GRL_OK after launching, a negative error, or +1 when this geometry cannot be expressed as TMA boxes (the
 // caller then launches the gather kernel of attn_tc.cu).  Arguments already validated by launch_attn_tc.

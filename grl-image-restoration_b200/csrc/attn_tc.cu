@@ -443,11 +443,10 @@ int attn_variant(int set) {
     // default 5: the persistent TMEM-resident kernel (attn2.cu) wherever the geometry has TMA boxes, this file's gather
     // kernel otherwise.  GRL_ATTN_SPLIT=0 forces the gather kernel (A/B runs, tools/attn_debug.py).
     const char* e = getenv("GRL_ATTN_SPLIT");
-    const int v = e ? atoi(e) : 5;
-    variant = (v >= 0 && v <= 5) ? v : 5;
+    variant = (e && atoi(e) == 0) ? 0 : 5;
   }
   const int prev = variant;
-  if (set >= 0 && set <= 5) variant = set;
+  if (set == 0 || set == 5) variant = set;
   return prev;
 }
 
@@ -464,13 +463,7 @@ int launch_attn_tc(const AttnTcArgs& a, cudaStream_t st) {
   const int Nq = a.gq.wh * a.gq.ww;
   const long long nblk = (long long)a.B * (a.gq.H / a.gq.wh) * (a.gq.W / a.gq.ww) * a.heads * ceil_div(Nq, kQT);
   GRL_REQUIRE(nblk < (1ll << 31), "attn_tc: grid too large");
-  const int split = attn_variant(-1);  // 1 | 2: experimental two-threads-per-row kernel (attn_tc_split.cu), default 0
-  if (split == 1 || split == 2) return launch_attn_tc_split(a, (unsigned)nblk, split, st);
-  if (split == 3 || split == 4) {  // TMA producer where the geometry allows it, else fall through to the gather kernel
-    const int rc = launch_attn_tc_tma(a, (unsigned)nblk, split == 4, st);
-    if (rc <= 0) return rc;
-  }
-  if (split == 5) {  // persistent TMEM-resident kernel (attn2.cu) where the geometry allows it
+  if (attn_variant(-1) == 5) {  // persistent TMEM-resident kernel (attn2.cu) where the geometry has TMA boxes
     const int rc = launch_attn2(a, st);
     if (rc <= 0) return rc;
   }

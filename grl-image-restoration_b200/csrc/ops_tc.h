@@ -85,16 +85,12 @@ struct AttnTcArgs {
   int ones_col;  // V[:, 31] == 1 for every key: take the softmax denominator from O[:, 31]
 };
 int launch_attn_tc(const AttnTcArgs& a, cudaStream_t st);
-// experimental two-threads-per-row variant (attn_tc_split.cu); reached through launch_attn_tc when the variant is 1|2
-int attn_variant(int set);  // -1 (or anything outside {0..4}): query only; returns the previous value
-int launch_attn_tc_split(const AttnTcArgs& a, unsigned nblk, int mode, cudaStream_t st);
-// experimental TMA-producer variants (attn_tc_tma.cu): 3, and 4 = 3 + bias rows staged in shared memory; returns +1 when
-// the geometry has no TMA box form
-int launch_attn_tc_tma(const AttnTcArgs& a, unsigned nblk, bool staged_bias, cudaStream_t st);
-int attn_tma_box_tokens(const GrlGrid& g);
+// 5 = attn2.cu where the geometry allows it (default), 0 = always this file's gather kernel; -1 (or anything else): query only
+int attn_variant(int set);
 // persistent warp-specialised kernel (attn2.cu): P and O in TMEM, NWG query tiles share each K / V tile; returns +1 when the
 // geometry has no TMA box form
 int launch_attn2(const AttnTcArgs& a, cudaStream_t st);
+int attn_tma_box_tokens(const GrlGrid& g);  // tokens per TMA box of attn2.cu for this grid, 0 = no box form
 int attn2_debug(int* out8);  // {timed_out, wait site, block, warp, parity, barrier smem offset, 0, 0} of the first timed-out wait; clears it
 
 }  // namespace tc

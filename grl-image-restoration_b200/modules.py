@@ -377,16 +377,22 @@ class EfficientMixAttnTransformerBlock(nn.Module):
     precision = "fp32"  # "fp32": exact-parity SIMT kernels; "fp16" / "bf16": fused tcgen05 path (tc.py)
 
     @torch.no_grad()
-    def forward(self, x, x_size, all_table_index_mask):
-        t = self._get_table_index_mask(all_table_index_mask)
-        if self.precision != "fp32":
-            from . import tc
+    def forward_tc(self, x32, x16, x_size, all_table_index_mask):
+        """Tensor-core path with the residual stream as an explicit PAIR: x32 fp32 (B, L, C) and its 16-bit operand copy
+        x16 (B, L, Cpad) (None: packed here).  Returns the pair of the block's output, so a stage / network chains
+        blocks without re-packing and without hiding state on tensors."""
+        from . import tc
 
-            K.capi.require_device(x)
-            x32 = x if x.is_contiguous() else x.contiguous()
-            y32, y16 = tc.block_plan(self, tc.FMT[self.precision]).run(self, x32, getattr(x, "_grl_bf16", None), x_size, t)
-            y32._grl_bf16 = y16  # operand copy for the next GEMM (saves a re-pack per block)
-            return y32
+        K.capi.require_device(x32)
+        t = self._get_table_index_mask(all_table_index_mask)
+        x32 = x32 if x32.is_contiguous() else x32.contiguous()
+        return tc.block_plan(self, tc.FMT[self.precision]).run(self, x32, x16, x_size, t)
+
+    @torch.no_grad()
+    def forward(self, x, x_size, all_table_index_mask):
+        if self.precision != "fp32":
+            return self.forward_tc(x, None, x_size, all_table_index_mask)[0]
+        t = self._get_table_index_mask(all_table_index_mask)
         u = self.attn(x, x_size, t)
         if self.args.local_connection:
             y, gate = self.conv.features_and_gate(x, x_size)
@@ -503,27 +509,35 @@ class TransformerStage(nn.Module):
                 raise NotImplementedError(f"Parameter initialization method {self.init_method} not implemented in TransformerStage.")
 
     @torch.no_grad()
+    def forward_tc(self, x32, x16, x_size, table_index_mask):
+        """Tensor-core path of the stage on the explicit (fp32 stream, 16-bit operand copy) pair; returns the pair."""
+        from . import tc
+
+        B, L, C = x32.shape
+        H, W = x_size
+        fmt = tc.FMT[self.blocks[0].precision]
+        cpad = tc.round_up(C, 64)
+        r32, r16 = x32, x16
+        for blk in self.blocks:
+            r32, r16 = blk.forward_tc(r32, r16, x_size, table_index_mask)
+        if r16 is None or r16.dtype != tc.DTYPE[fmt]:
+            r16 = tc.pack_rows(r32.contiguous(), cpad, fmt)
+        plan = tc.conv_plan(self, "conv", self.conv, cpad, fmt)
+        out32 = torch.empty(B, L, C, device=x32.device, dtype=torch.float32)
+        out16 = torch.empty(B, L, cpad, device=x32.device, dtype=tc.DTYPE[fmt])
+        tc.conv3x3(r16.view(B, H, W, cpad), plan.w, plan.b, cpad, plan.npad, n_store=cpad, n_real=C, out_bf16=out16,
+                   out_f32=out32, res_f32=x32.contiguous())
+        return out32, out16
+
+    @torch.no_grad()
     def forward(self, x, x_size, table_index_mask):
+        if len(self.blocks) and self.blocks[0].precision != "fp32":
+            return self.forward_tc(x, None, x_size, table_index_mask)[0]
         res = x
         for blk in self.blocks:
             res = blk(res, x_size, table_index_mask)
         B, L, C = x.shape
         H, W = x_size
-        if len(self.blocks) and self.blocks[0].precision != "fp32":
-            from . import tc
-
-            fmt = tc.FMT[self.blocks[0].precision]
-            cpad = tc.round_up(C, 64)
-            r16 = getattr(res, "_grl_bf16", None)
-            if r16 is None or r16.dtype != tc.DTYPE[fmt]:
-                r16 = tc.pack_rows(res.contiguous(), cpad, fmt)
-            plan = tc.conv_plan(self, "conv", self.conv, cpad, fmt)
-            out32 = torch.empty(B, L, C, device=x.device, dtype=torch.float32)
-            out16 = torch.empty(B, L, cpad, device=x.device, dtype=tc.DTYPE[fmt])
-            tc.conv3x3(r16.view(B, H, W, cpad), plan.w, plan.b, cpad, plan.npad, n_store=cpad, n_real=C, out_bf16=out16,
-                       out_f32=out32, res_f32=x.contiguous())
-            out32._grl_bf16 = out16
-            return out32
         return conv2d_cl(self.conv, self._pack, res.view(B, H, W, C), res=x.view(B, H, W, C)).view(B, L, C)
 
 
@@ -617,6 +631,11 @@ class GRL(nn.Module):
         else:
             self.conv_last = nn.Conv2d(embed_dim, out_channels, 3, 1, 1)
         self._packs = {}
+        self._mean_list = [float(v) for v in self.mean.flatten().tolist()]  # host copy (no device sync in forward)
+        self._graphs = {}
+        # opt-in CUDA-graph replay of the tensor-core forward (one captured graph per input shape): a forward is ~540
+        # launches, which bounds small batches (one 256x256 Base tile) by launch latency, not by the kernels
+        self.use_cuda_graph = os.environ.get("GRL_B200_CUDA_GRAPH", "0") == "1"
 
         self.apply(self._init_weights)
         if init_method in ["l", "w"] or init_method.find("t") >= 0:
@@ -755,8 +774,8 @@ class GRL(nn.Module):
         cpad = tc.round_up(C, 64)
         s = self.upscale
         need_res = self.upsampler not in ("pixelshuffle", "pixelshuffledirect", "nearest+conv") and self.in_channels == self.out_channels
-        x16, xc32 = tc.head_pack(x, Hp, Wp, self.mean, self.img_range, 64, fmt, want_f32=need_res)
-        mean = [float(v) for v in self.mean.flatten().tolist()]
+        mean = self._mean_list
+        x16, xc32 = tc.head_pack(x, Hp, Wp, mean, self.img_range, 64, fmt, want_f32=need_res)
         shift = mean if len(mean) > 1 else mean * 4
 
         def conv(name, module, inp16, cin_pad, *, act=K.ACT_NONE, slope=0.0, res=None, want_f32=False, want16=True, ps_r=0,
@@ -781,8 +800,9 @@ class GRL(nn.Module):
         feat = f32.view(B, Hp * Wp, C)
         t = K.ln_residual(None, feat, self.norm_start.weight, self.norm_start.bias, self.norm_start.eps)
         tim = self.get_table_index_mask(dev, (Hp, Wp))
+        t16 = None  # 16-bit operand copy of the residual stream, carried explicitly from block to block
         for layer in self.layers:
-            t = layer(t, (Hp, Wp), tim)
+            t, t16 = layer.forward_tc(t, t16, (Hp, Wp), tim)
         t = K.ln_residual(None, t, self.norm_end.weight, self.norm_end.bias, self.norm_end.eps)
         t16 = tc.pack_rows(t, cpad, fmt).view(B, Hp, Wp, cpad)
         body16, _ = conv("conv_after_body", self.conv_after_body, t16, cpad, res=f32)
@@ -806,6 +826,44 @@ class GRL(nn.Module):
             y, _ = conv("conv_last", self.conv_last, body16, cpad, res=xc32, final_r=1)
         return y
 
+    # ---- CUDA graphs ----------------------------------------------------------------------------
+    def reset_cuda_graphs(self):
+        """Drops every captured graph (they bake in the addresses of the packed weights and of their static buffers)."""
+        self._graphs = {}
+
+    def _apply(self, fn, *args, **kwargs):  # .to() / .cuda() / .half() move parameters: captured graphs are stale
+        self._graphs = {}
+        return super()._apply(fn, *args, **kwargs)
+
+    def load_state_dict(self, *args, **kwargs):
+        self._graphs = {}
+        return super().load_state_dict(*args, **kwargs)
+
+    @torch.no_grad()
+    def _forward_graphed(self, x):
+        """Replays a captured graph of _forward_bf16 for this input shape (captures it on first use, after two eager
+        warm-up forwards that build the packed weights / bias tables / kernel attributes).  The result is a fresh tensor
+        (the caller may mutate it in place, engines/base.py:113)."""
+        key = (tuple(x.shape), x.device.index, self.precision)
+        ent = self._graphs.get(key)
+        if ent is None:
+            static_in = x.clone()
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    self._forward_bf16(static_in)
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                static_out = self._forward_bf16(static_in)
+            ent = (graph, static_in, static_out)
+            self._graphs[key] = ent
+        graph, static_in, static_out = ent
+        static_in.copy_(x)
+        graph.replay()
+        return static_out.clone()
+
     def forward_features(self, x):
         """(B, C, H, W) -> (B, C, H, W) like the reference."""
         K.capi.require_device(x)
@@ -816,7 +874,9 @@ class GRL(nn.Module):
         K.capi.require_device(x)
         H, W = x.shape[2:]
         if self.precision != "fp32":
-            return self._forward_bf16(x.float().contiguous()).to(x.dtype)
+            xin = x.float().contiguous()
+            y = self._forward_graphed(xin) if self.use_cuda_graph else self._forward_bf16(xin)
+            return y.to(x.dtype)
         x = self.check_image_size(x)
         self.mean = self.mean.type_as(x)
         x = ((x - self.mean) * self.img_range).float()

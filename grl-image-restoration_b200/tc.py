@@ -52,7 +52,7 @@ def head_pack(x, hp, wp, mean, img_range, cpad=64, fmt=0, want_f32=False):
     B, Cin, H, W = x.shape
     y16 = _h16(B, hp, wp, cpad, device=x.device, fmt=fmt)
     y32 = torch.empty(B, hp, wp, Cin, device=x.device, dtype=torch.float32) if want_f32 else None
-    m = [float(v) for v in mean.flatten().tolist()]
+    m = [float(v) for v in (mean if isinstance(mean, (list, tuple)) else mean.flatten().tolist())]
     m = (m * 4)[:4] if len(m) == 1 else (m + [0.0] * 4)[:4]
     arr = (ctypes.c_float * 4)(*m)
     capi.check(capi.lib().grl_tc_head_pack(capi.ptr(x), B, Cin, H, W, hp, wp, arr, float(img_range), capi.ptr(y16), cpad,

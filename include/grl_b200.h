@@ -64,7 +64,7 @@ int grl_coords_table_host(int wh, int ww, int df, float* out);
  * (nW, wh*ww) int32, the flat index y*W + x (un-rolled image) of token n of window w -- the addressing every attention
  * kernel folds into its loads and stores. */
 int grl_token_map_host(GrlGrid g, int32_t* out);
-/* Tokens per TMA box of the experimental TMA-producer attention kernel for this grid (attn_tc_tma.cu): runs of that many
+/* Tokens per TMA box of the persistent attention kernel for this grid (csrc/attn2.cu): runs of that many
  * tokens starting at multiples of it are contiguous in memory for every window.  0 = no box form (gather kernel). */
 int grl_tc_attn_box_tokens(GrlGrid g);
 
@@ -243,11 +243,12 @@ typedef struct {
 } GrlTcAttn;
 int grl_tc_attn(const GrlTcAttn* p, void* stream);
 
-/* Kernel variant behind grl_tc_attn: 0 = one thread per query row, cp.async gathers (default); EXPERIMENTAL: 1 / 2 = two
- * threads per row at 2 / 3 CTAs per SM (attn_tc_split.cu), 3 = Q / K / V tiles fetched with TMA tensor copies, 4 = 3 +
- * the bias rows of every key tile staged in shared memory by bulk copies (attn_tc_tma.cu; geometries without a box form
- * run variant 0).  Initial value: environment variable GRL_ATTN_SPLIT
- * (unset = 0).  Returns the previous value; a value outside {0..4} only queries.  Same results contract as variant 0. */
+/* Kernel behind grl_tc_attn: 5 (default) = the persistent warp-specialised kernel of csrc/attn2.cu -- Q / K / V tiles by TMA
+ * boxes of the (B, H, W, C) tensors, S and P in TMEM (P V reads its A operand from TMEM), O accumulated in TMEM with a lazy
+ * rescale, several query tiles sharing every K / V tile -- for every geometry whose rolled window rows split into runs of
+ * >= 8 contiguous tokens (grl_tc_attn_box_tokens > 0); other geometries, and 0, run the gather kernel of csrc/attn_tc.cu
+ * (one CTA per 128-query tile, cp.async row gathers).  Initial value: environment variable GRL_ATTN_SPLIT (unset = 5).
+ * Returns the previous value; anything but 0 / 5 only queries.  Both kernels compute the same function. */
 int grl_tc_attn_variant(int variant);
 /* Diagnosis of the persistent attention kernel's pipeline: out8 = {1 if an mbarrier wait timed out (~0.5 s) since the last
  * call, wait site id (csrc/attn2.cu), block, warp, parity, barrier shared-memory offset, 0, 0}; reading clears it.  A timed-out

@@ -122,3 +122,27 @@ def test_head_tail_fusion_all_heads(pkg, oracle, cases, device, name):
     b = m(xo)
     assert a.shape == b.shape
     assert (-10 * torch.log10(((a - b) ** 2).mean())).item() >= 50.0
+
+
+def test_cuda_graph_replay_matches_eager(pkg, oracle, device):
+    """GRL.use_cuda_graph: the captured graph of the tensor-core forward replays bit-identically to the eager launch
+    sequence, for new inputs of the captured shape, a second shape gets its own graph, and the caller may mutate the
+    result in place (engines/base.py:113) without touching the graph's static buffers."""
+    cfg = pkg.configs.grl_config("base", "sr", 4, 64)
+    m = build(pkg, oracle, cfg, device, seed=3, precision="fp16", style="init")
+    x1 = oracle.synth_input((2, 3, 64, 64), seed=5).to(device)
+    x2 = oracle.synth_input((2, 3, 64, 64), seed=6).to(device)
+    e1, e2 = m(x1).clone(), m(x2).clone()
+    m.use_cuda_graph = True
+    g1 = m(x1)
+    g1_copy = g1.clone()
+    g1.clamp_(0, 0.1)  # in-place mutation by the caller
+    g2 = m(x2)
+    g1b = m(x1)
+    assert torch.equal(g1_copy, e1) and torch.equal(g2, e2) and torch.equal(g1b, e1)
+    x3 = oracle.synth_input((1, 3, 64, 128), seed=7).to(device)  # another shape: another graph
+    g3 = m(x3)
+    m.use_cuda_graph = False
+    assert torch.equal(g3, m(x3)) and len(m._graphs) == 2
+    m.load_state_dict(oracle.synth_state_dict(cfg, seed=4, style="init"), strict=False)
+    assert len(m._graphs) == 0  # new weights: stale graphs are dropped

@@ -21,10 +21,10 @@ def bf(t, fmt=0):
     return t.to(torch.bfloat16 if fmt else torch.float16).float()
 
 
-# Attention kernel variants (grl_tc_attn_variant): 0 = production.  The experimental kernels (1, 2: two threads per row;
-# 3: TMA producer) are exercised by the same tests only on request -- GRL_TEST_EXPERIMENTAL=1 -- because a faulting experimental kernel
-# would poison the CUDA context of the whole pytest process.
-ATTN_VARIANTS = [0, 1, 2, 3, 4] if os.environ.get("GRL_TEST_EXPERIMENTAL") == "1" else [None]  # None: whatever GRL_ATTN_SPLIT says
+# Both attention kernels behind grl_tc_attn are production code and are exercised by the same tests: 5 = the persistent
+# TMA / TMEM kernel (csrc/attn2.cu, default; geometries without TMA boxes fall through to the other one), 0 = the gather
+# kernel (csrc/attn_tc.cu) forced for every geometry.
+ATTN_VARIANTS = [5, 0]
 
 
 @pytest.fixture(scope="module", params=ATTN_VARIANTS, ids=lambda v: "attn" if v is None else f"attn{v}")

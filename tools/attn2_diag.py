@@ -15,9 +15,8 @@ AB = os.path.join(ROOT, "ab")
 STUB = "-DGRL_A2_DIAG_NOBIAS -DGRL_A2_DIAG_NOEXP -DGRL_A2_DIAG_NOLDTM -DGRL_A2_DIAG_NOSTTM -DGRL_A2_DIAG_NOMAX"
 VARIANTS = {
     "base": "",
-    "bgsleep": "-DGRL_A2_BG_SLEEP",
+    "multi_issuer": "-DGRL_A2_MULTI_ISSUER",
     "stub": STUB,
-    "stub_bgsleep": STUB + " -DGRL_A2_BG_SLEEP",
 }
 
 
