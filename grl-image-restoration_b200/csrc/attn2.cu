@@ -22,6 +22,7 @@
 // TWO tiles ahead of the softmax: the issuer sends  P V_g(t) ; Q K^T_g(t+2)  back to back -- both touch buffer t & 1, and
 // the tensor pipe executes one thread's MMAs in issue order, so the second overwrites what the first has read -- which
 // means S_g(t+1) is already complete when the softmax warps finish tile t: they never wait for the MMA round trip.
+#include <type_traits>
 #include <stdlib.h>
 
 #include <algorithm>
@@ -113,6 +114,7 @@ struct A2Geom {
   int n_qg;         // query groups (NWG * 128 rows) per window
   int per_head;     // B * windows * n_qg work items per head; CTA b works on head b / (gridDim / heads)
   int stages;       // K / V ring depth
+  int ntiles;       // key tiles per window: ceil(Nk / 64) (host-computed: one constant load instead of a divide chain per tile)
 };
 
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
@@ -144,7 +146,7 @@ __device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64
 // g_a2_dbg and raises an abort flag; every wait then falls through, the kernel finishes with garbage and the host can
 // read the record (grl_tc_attn2_debug).
 __device__ int g_a2_dbg[8];
-__device__ __forceinline__ void mbar_wait2(uint64_t* bar, uint32_t parity, int site = 0) {
+__device__ __forceinline__ void mbar_wait2_sa(uint32_t bar_sa, uint32_t parity, int site = 0) {  // bar_sa: shared-window address
   uint32_t ok;
   int spins = 0;
   long long t0 = 0;
@@ -155,7 +157,7 @@ __device__ __forceinline__ void mbar_wait2(uint64_t* bar, uint32_t parity, int s
         "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
+        : "r"(bar_sa), "r"(parity)
         : "memory");
 #else
     asm volatile(
@@ -163,7 +165,7 @@ __device__ __forceinline__ void mbar_wait2(uint64_t* bar, uint32_t parity, int s
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
+        : "r"(bar_sa), "r"(parity)
         : "memory");
 #endif
     if (ok) return;
@@ -174,13 +176,18 @@ __device__ __forceinline__ void mbar_wait2(uint64_t* bar, uint32_t parity, int s
       else if (now - t0 > 1000000000ll) {
         if (atomicCAS(&g_a2_dbg[0], 0, 1) == 0) {
           g_a2_dbg[1] = site, g_a2_dbg[2] = blockIdx.x, g_a2_dbg[3] = threadIdx.x >> 5, g_a2_dbg[4] = (int)parity;
-          g_a2_dbg[5] = (int)(smem_u32(bar) & 0xffff);
+          g_a2_dbg[5] = (int)(bar_sa & 0xffff);
           __threadfence();
         }
         return;
       }
     }
   }
+}
+
+__device__ __forceinline__ void mbar_wait2(uint64_t* bar, uint32_t parity, int site = 0) { mbar_wait2_sa(smem_u32(bar), parity, site); }
+__device__ __forceinline__ void mbar_arrive_sa(uint32_t bar_sa) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_sa) : "memory");
 }
 
 // Warp-collective wait (call sites are warp-uniform).
@@ -219,6 +226,20 @@ __device__ __forceinline__ int lds32i(uint32_t saddr) {
   int v;
   asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(saddr));
   return v;
+}
+
+// packed fp32 pairs (sm_100 FADD2: two adds per issued instruction; the softmax warps are issue / latency bound)
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
+  uint64_t d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(lo), "f"(hi));
+  return d;
+}
+__device__ __forceinline__ float lo2(uint64_t v) { return __uint_as_float((uint32_t)v); }
+__device__ __forceinline__ float hi2(uint64_t v) { return __uint_as_float((uint32_t)(v >> 32)); }
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
 }
 
 __device__ __forceinline__ float fmax3(float a, float b, float c) {
@@ -288,7 +309,7 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
   const int nww = a.gq.W / a.gq.ww, nwh = a.gq.H / a.gq.wh;
   const int nW = nwh * nww;
   const int Wt = a.gq.ww + a.gk.ww - 1;
-  const int ntiles = (Nk + KT - 1) / KT;
+  const int ntiles = tg.ntiles;
   static_assert(NWG * kColsPerWg <= 512, "two S buffers + O per warpgroup: at most 3 warpgroups fit the 512 TMEM columns");
   constexpr uint32_t TMEM_COLS = (NWG * kColsPerWg <= 128) ? 128 : (NWG * kColsPerWg <= 256) ? 256 : 512;
   constexpr int fmt = (VAR & 1) ? FMT_BF16 : FMT_F16;
@@ -369,7 +390,7 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
       Ring rp = {0, 0};
 #pragma unroll
       for (int g = 0; g < NWG; ++g) q_cnt[g] = 0;
-      if (BS && lane == 0) {  // the head's table: 4 shifted copies, contiguous in global memory, one bulk copy
+      if (BS && elect_one()) {  // the head's table: 4 shifted copies, contiguous in global memory, one bulk copy
         const uint32_t bytes = 16u * (uint32_t)a.rows_pad;
         mbar_expect_tx(bias_full, bytes);
         bulk_load_1d(bias_s, a.bias + (size_t)my_h * 4 * a.rows_pad, bytes, bias_full);
@@ -384,7 +405,7 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
             ++q_cnt[g];
             const int q0 = (it.qg * NWG + g) * kQT;
             const int cnt = min(kQT, Nq - q0);
-            if (lane == 0) {
+            if (elect_one()) {
               mbar_expect_tx(&q_full[g], (uint32_t)A2_BOXCNT(cnt, tg.bw_q) * 64u);
               Cur cq = {q0 / a.gq.ww, q0 % a.gq.ww};
               tma_run(&tmQ, a.q_off + it.h * kDP, Qs + g * S::Q_BYTES, nullptr, 0, nullptr, a.gq, it, cq, cnt, tg.bw_q, &q_full[g]);
@@ -413,8 +434,8 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
             }
           }
           __syncwarp();  // every lane's koff / rid stores are ordered before lane 0's release
-          if (lane == 0) mbar_arrive(&meta_full[st]);
-          if (lane == 0) {
+          if (elect_one()) mbar_arrive(&meta_full[st]);
+          if (elect_one()) {
             mbar_expect_tx(&kv_full[st], (uint32_t)(A2_BOXCNT(cnt, tg.bw_k) + (a.v_dense ? KT : A2_BOXCNT(cnt, tg.bw_k))) * 64u);
             if (a.v_dense) {  // V = (B_, heads, Nk, 32) rows: one 2-D box (rows past this head's Nk: next head / zero fill, P == 0)
               tma_run(&tmK, a.k_off + it.h * kDP, kd, nullptr, 0, nullptr, a.gk, it, ck, cnt, tg.bw_k, &kv_full[st]);
@@ -442,7 +463,7 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
       const uint64_t k_desc0 = umma_desc(smem_u32(Ks), 16, 512, SWZ_64B);
       const uint64_t v_desc0 = umma_desc(smem_u32(Vs), 16, 512, SWZ_64B);
       const uint32_t wg_ta = tmem + g * kColsPerWg;
-      uint32_t kv_it = 0, q_cnt = 0, p_cnt[2] = {0, 0}, d_cnt = 0;
+      uint32_t kv_it = 0, q_cnt = 0, p_par = 0, d_cnt = 0;  // p_par: bit b = parity to wait for on p_full[2 g + b]
       Ring r0 = {0, 0}, r2 = {0, 0}, rl = {0, 0};  // tile t, tile t + 2, last tile handled
       r2.adv(NS);
       r2.adv(NS);
@@ -464,14 +485,14 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
         for (int t0 = 0; t0 < 2 && t0 < ntiles; ++t0, rq.adv(NS)) {
           const int st = rq.st;
           mbar_wait_bg(&kv_full[st], rq.ph, 4);
-          if (active && lane == 0) {
+          if (active && elect_one()) {
             tcgen05_fence_after();
             issue_qk(st, t0, t0 + 1 == ntiles);
             umma_commit(&bar_s[2 * g + t0]);
           }
           __syncwarp();
         }
-        if (ntiles == 1 && active && lane == 0) umma_commit(&bar_s[2 * g + 1]);  // keep both buffers' counts in step
+        if (ntiles == 1 && active && elect_one()) umma_commit(&bar_s[2 * g + 1]);  // keep both buffers' counts in step
         __syncwarp();
         for (int t = 0; t < ntiles; ++t, ++kv_it, rl = r0, r0.adv(NS), r2.adv(NS)) {
           const int st = r0.st, st2 = r2.st;
@@ -479,9 +500,9 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
           if (active) {
             // (per S buffer: the softmax warps run up to two tiles ahead of this thread, and an mbarrier that completes
             // twice before its waiter has looked is indistinguishable from one that has not completed)
-            mbar_wait_bg(&p_full[2 * g + (t & 1)], p_cnt[t & 1] & 1, 6);
-            ++p_cnt[t & 1];
-            if (lane == 0) {
+            mbar_wait_bg(&p_full[2 * g + (t & 1)], (p_par >> (t & 1)) & 1u, 6);
+            p_par ^= 1u << (t & 1);
+            if (elect_one()) {
               tcgen05_fence_after();
               const uint64_t vd = v_desc0 + (uint64_t)(st * (S::KV_BYTES >> 4));
               const uint32_t p_ta = wg_ta + (t & 1) * 64;
@@ -491,7 +512,7 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
               umma_commit(&bar_s[2 * g + (t & 1)]);  // P V(t) done (+ S(t+2) ready)
               A2_KVCOMMIT(&kv_empty[st]);            // every MMA of this warpgroup that reads stage st has been issued
             }
-          } else if (lane == 0) {
+          } else if (elect_one()) {
             mbar_arrive(&kv_empty[st]);  // sitting this item out: release the stage (after its fill: kv_full(st2) / prologue waits)
           }
           __syncwarp();
@@ -517,9 +538,8 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
       const uint64_t q_desc0 = umma_desc(smem_u32(Qs), 16, 512, SWZ_64B);
       const uint64_t k_desc0 = umma_desc(smem_u32(Ks), 16, 512, SWZ_64B);
       const uint64_t v_desc0 = umma_desc(smem_u32(Vs), 16, 512, SWZ_64B);
-      uint32_t kv_it = 0, q_cnt[NWG], p_cnt[NWG][2], d_cnt[NWG];
-#pragma unroll
-      for (int g = 0; g < NWG; ++g) q_cnt[g] = 0, p_cnt[g][0] = 0, p_cnt[g][1] = 0, d_cnt[g] = 0;
+      // parities to wait for, one bit per barrier (arrays indexed by t & 1 would live in local memory)
+      uint32_t kv_it = 0, q_par = 0, p_par = 0, d_par = 0;
       Ring r0 = {0, 0}, r2 = {0, 0}, rl = {0, 0};  // tile t, tile t + 2, last tile handled
       r2.adv(NS);
       r2.adv(NS);
@@ -541,10 +561,10 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
           for (int g = 0; g < NWG; ++g) {
             if (g < it.nact) {
               if (t0 == 0) {
-                mbar_wait_bg(&q_full[g], q_cnt[g] & 1, 3);
-                ++q_cnt[g];
+                mbar_wait_bg(&q_full[g], (q_par >> g) & 1u, 3);
+                q_par ^= 1u << g;
               }
-              if (lane == 0) {
+              if (elect_one()) {
                 tcgen05_fence_after();
                 issue_qk(g, st, t0, t0 + 1 == ntiles);
                 umma_commit(&bar_s[2 * g + t0]);
@@ -557,14 +577,13 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
         for (int t = 0; t < ntiles; ++t, ++kv_it, rl = r0, r0.adv(NS), r2.adv(NS)) {
           const int st = r0.st, st2 = r2.st;
           if (t + 2 < ntiles) mbar_wait_bg(&kv_full[st2], r2.ph, 5);
+#ifndef GRL_A2_ILV  // default: one warpgroup after the other, each as soon as its P is there (the warpgroups need not run in step)
 #pragma unroll
           for (int g = 0; g < NWG; ++g) {
             if (g < it.nact) {
-              // (per S buffer: the softmax warps run up to two tiles ahead of this thread, and an mbarrier that completes
-              // twice before its waiter has looked is indistinguishable from one that has not completed)
-              mbar_wait_bg(&p_full[2 * g + (t & 1)], p_cnt[g][t & 1] & 1, 6);
-              ++p_cnt[g][t & 1];
-              if (lane == 0) {
+              mbar_wait_bg(&p_full[2 * g + (t & 1)], (p_par >> (2 * g + (t & 1))) & 1u, 6);
+              p_par ^= 1u << (2 * g + (t & 1));
+              if (elect_one()) {
                 tcgen05_fence_after();
                 const uint64_t vd = v_desc0 + (uint64_t)(st * (S::KV_BYTES >> 4));
                 const uint32_t wg_ta = tmem + g * kColsPerWg;
@@ -577,14 +596,56 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
               __syncwarp();
             }
           }
-          if (lane == 0) A2_KVCOMMIT(&kv_empty[st]);  // every MMA that reads stage st has been issued
+#else
+          // (per S buffer: the softmax warps run up to two tiles ahead of this thread, and an mbarrier that completes
+          // twice before its waiter has looked is indistinguishable from one that has not completed)
+#pragma unroll
+          for (int g = 0; g < NWG; ++g) {
+            if (g < it.nact) {
+              mbar_wait_bg(&p_full[2 * g + (t & 1)], (p_par >> (2 * g + (t & 1))) & 1u, 6);
+              p_par ^= 1u << (2 * g + (t & 1));
+            }
+          }
+          if (elect_one()) {
+            // A/B build (GRL_A2_ILV): the MMAs of the three warpgroups interleaved k-step by k-step, so that consecutive
+            // MMAs are independent.  Measured: no gain (1.71 vs 1.66 ms) -- the tensor pipe is not what the hand-off waits for.
+            tcgen05_fence_after();
+            const uint64_t vd = v_desc0 + (uint64_t)(st * (S::KV_BYTES >> 4));
+            const uint64_t kd2 = k_desc0 + (uint64_t)(st2 * (S::KV_BYTES >> 4));
+            const uint32_t bo = (uint32_t)(t & 1) * 64u;
+#pragma unroll
+            for (int k = 0; k < KT / 16; ++k) {
+#pragma unroll
+              for (int g = 0; g < NWG; ++g)
+                if (g < it.nact) A2_PV(umma_ts(tmem + g * kColsPerWg + 128, tmem + g * kColsPerWg + bo + k * 8, vd + (uint64_t)(k * 64), idesc_pv, (t | k) != 0));
+            }
+            if (t + 2 < ntiles) {
+#pragma unroll
+              for (int k = 0; k < 2; ++k) {
+#pragma unroll
+                for (int g = 0; g < NWG; ++g)
+                  if (g < it.nact) A2_QK(umma_ss(tmem + g * kColsPerWg + bo, q_desc0 + (uint64_t)(g * (S::Q_BYTES >> 4)) + 2 * k, kd2 + 2 * k, idesc_qk, k != 0));
+              }
+              if (t + 3 == ntiles) {
+#pragma unroll
+                for (int g = 0; g < NWG; ++g)
+                  if (g < it.nact) umma_commit(&q_empty[g]);
+              }
+            }
+#pragma unroll
+            for (int g = 0; g < NWG; ++g)
+              if (g < it.nact) umma_commit(&bar_s[2 * g + (t & 1)]);  // P V(t) done (+ S(t+2) ready)
+          }
+          __syncwarp();
+#endif
+          if (elect_one()) A2_KVCOMMIT(&kv_empty[st]);  // every MMA that reads stage st has been issued
           __syncwarp();
         }
 #pragma unroll
         for (int g = 0; g < NWG; ++g) {
           if (g < it.nact) {  // the warpgroup has consumed this item's closing completions of bar_s (see its epilogue)
-            mbar_wait_bg(&item_done[g], d_cnt[g] & 1, 7);
-            ++d_cnt[g];
+            mbar_wait_bg(&item_done[g], (d_par >> g) & 1u, 7);
+            d_par ^= 1u << g;
           }
         }
       }
@@ -595,11 +656,22 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
   } else {
     // =============================================================== softmax warpgroups: thread = query row
     const int row = tid & 127;
-    const uint32_t ts0 = tmem + ((uint32_t)((warp & 3) * 32) << 16) + wg * kColsPerWg;  // S / P buffer 0 of this row
+#ifdef GRL_A2_SKEW  // A/B: start warpgroup g  g * GRL_A2_SKEW  cycles late, so that the warpgroups' MUFU / LSU phases do not coincide
+    if (wg > 0) {
+      const long long t_start = clock64();
+      while (clock64() - t_start < (long long)wg * GRL_A2_SKEW) {
+      }
+    }
+#endif
+    uint32_t ts0 = tmem + ((uint32_t)((warp & 3) * 32) << 16) + wg * kColsPerWg;  // S / P buffer 0 of this row
+    asm volatile("" : "+r"(ts0));  // opaque: kept in a register instead of being rebuilt from %tid (S2R + shifts) every tile
     const uint32_t to = ts0 + 128;                                                        // O columns
     bool bias_ready = false;
     const uint32_t bias_sa = smem_u32(bias_s), koff_sa = smem_u32(koff_s), krid_sa = smem_u32(krid_s);
-    uint32_t s_cnt[2] = {0, 0};  // completions consumed per S buffer (every tile consumes exactly one)
+    // shared-window addresses of this warpgroup's barriers, computed once (a generic pointer costs a window-base computation
+    // per use: S2UR CgaCtaId / ULEA / ... on the per-tile critical path)
+    const uint32_t bar_s_sa = smem_u32(&bar_s[2 * wg]), p_full_sa = smem_u32(&p_full[2 * wg]);
+    uint32_t s_par = 0;  // bit b: parity of the next completion of bar_s[2 wg + b] (every tile consumes exactly one)
     Ring rs = {0, 0};
     for (int item = my_c; item < tg.per_head; item += cph) {
       const Item it = decode(item);
@@ -631,119 +703,232 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
         const int k0 = t * KT, st = rs.st, buf = t & 1;
         const uint32_t ts = ts0 + buf * 64;
         const bool full_tile = (KW > 0) && (k0 + KT <= Nk);
-        // ---- x = bias (+ mask) - m_ref first: these loads and adds do not depend on S and run while Q K^T is in flight.
-        // Nothing here may touch the per-stage metadata: a warpgroup that sat out the previous item is a whole item
-        // ahead of the producer, and an mbarrier parity wait only orders phases that are at most one apart.
-        float x[KT];
-        if (full_tile) {
-          constexpr int KWS = KW > 0 ? KW : 4;
-          constexpr int RW = (KWS >= 32) ? 32 : KWS;  // consecutive keys of one key row
-#pragma unroll
-          for (int r0 = 0; r0 < KT; r0 += RW) {
-            const int kj = k0 + r0;  // first key of the run (CTA-uniform, multiple of 4)
-            const int kh = kj / KWS, kw0 = kj % KWS;
-            const int s0 = base_i - (kh * Wt + kw0) - 3;  // table index of key kj + 3
-            const int cpy = (-s0) & 3;
-            const float4* bp = reinterpret_cast<const float4*>(bias_h + (size_t)cpy * a.rows_pad + (s0 + cpy));
-            const uint32_t bps = bias_sa + (uint32_t)(cpy * a.rows_pad + (s0 + cpy)) * 4u;  // BS: LDS.128
-            float off_lo = m_ref, off_hi = m_ref;
-            if (need_mask && mask_fast) {
-              const int rid_lo = 3 * ((int)a1 + (int)(kh >= kh_th)) + (int)b1;
-              off_lo = (rid_lo != q_rid) ? m_ref - kMaskLog2 : m_ref;
-              off_hi = (rid_lo + 1 != q_rid) ? m_ref - kMaskLog2 : m_ref;
-            }
-#pragma unroll
-            for (int qd = 0; qd < RW / 4; ++qd) {
-              const float4 bb = A2_BIAS(BS ? lds128(bps - 16u * qd) : __ldg(bp - qd));
-              const int j = r0 + 4 * qd;
-              const float off = (kw0 + 4 * qd >= kw_th) ? off_hi : off_lo;
-              x[j + 0] = bb.w - off, x[j + 1] = bb.z - off, x[j + 2] = bb.y - off, x[j + 3] = bb.x - off;
-            }
-          }
-        }
-        // ---- S_t
-        mbar_wait_warp(&bar_s[2 * wg + buf], s_cnt[buf] & 1, 10);
-        ++s_cnt[buf];
-        tcgen05_fence_after();
-        const bool meta_mask = need_mask && !(full_tile && mask_fast);
-        if (!full_tile || meta_mask) mbar_wait_warp(&meta_full[st], rs.ph, 11);  // S_t ready => this fill is the current one
-        if (!full_tile) {
-#pragma unroll
-          for (int j = 0; j < KT; ++j) x[j] = (BS ? lds32f(bias_sa + 4u * (uint32_t)(base_i - lds32i(koff_sa + 4u * (st * KT + j))))
-                       : __ldg(bias_h + base_i - lds32i(koff_sa + 4u * (st * KT + j)))) - m_ref;
-        }
-#pragma unroll
-        for (int c0 = 0; c0 < KT; c0 += 32) {
-          A2_LDTM({
-            uint32_t v[32];
-            tmem_ld32(ts + c0, v);
-            tmem_ld_wait();
-            _Pragma("unroll") for (int j = 0; j < 32; ++j) x[c0 + j] += __uint_as_float(v[j]);
-          })
-        }
-        if (meta_mask) {
-#pragma unroll
-          for (int j = 0; j < KT; ++j)
-            if (lds32i(krid_sa + 4u * (st * KT + j)) != q_rid) x[j] += kMaskLog2;
-        }
-        if (k0 + KT > Nk) {  // after the add: K rows past Nk are stale shared memory, S there may be anything
-#pragma unroll
-          for (int j = 0; j < KT; ++j)
-            if (k0 + j >= Nk) x[j] = -INFINITY;
-        }
-        float mx0 = fmax3(x[0], x[1], x[2]), mx1 = fmax3(x[3], x[4], x[5]);
-#pragma unroll
-        for (int j = 6; j + 3 < KT; j += 4) {
-          mx0 = fmax3(mx0, x[j], x[j + 1]);
-          mx1 = fmax3(mx1, x[j + 2], x[j + 3]);
-        }
-        const float mx = A2_MAX(fmax3(mx0, mx1, fmaxf(x[KT - 2], x[KT - 1])));
-        // ---- lazy rescale: move the reference only when a row outgrew it by 2^kTau (always on the first tile)
-        const bool first = (t == 0);
-        if (__any_sync(0xffffffffu, first || mx > kTau)) {
-          float delta = first ? mx : fmaxf(mx, 0.f);
-          if (!(fabsf(delta) < 1e30f)) delta = 0.f;  // rows of a partial query tile hold garbage
-          m_ref += delta;
-#pragma unroll
-          for (int j = 0; j < KT; ++j) x[j] -= delta;
-          if (!first) {
-            // O_g must hold P V of every tile < t.  The NEXT completion of the other buffer's barrier (S(t+1) ready, or the
-            // closing completion when t is the last tile) is committed right after P V(t-1): peek at it (the wait at tile
-            // t+1 / in the epilogue consumes it), which keeps the wait exact and off the common path.
-            mbar_wait_warp(&bar_s[2 * wg + (buf ^ 1)], s_cnt[buf ^ 1] & 1, 12);
-            tcgen05_fence_after();
-            const float sc = ex2(-delta);
-            uint32_t v[32];
-            tmem_ld32(to, v);
-            tmem_ld_wait();
-#pragma unroll
-            for (int e = 0; e < kDP; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) * sc);
-            tmem_st32(to, v);
-            l_run *= sc;
-          }
-        }
-        // ---- P_t = exp2(x) -> 16-bit pairs -> TMEM (over S_t)
+        // Tiles whose bias row is a closed-form run (full tile of a rectangular window, mask absent or closed-form) take the
+        // single-pass path below; ragged tiles / metadata masks keep the two-phase path after it.
+        const bool fastp = full_tile && (!need_mask || mask_fast);
         uint32_t pk[32];
-        float ps0 = 0.f, ps1 = 0.f;
+        if (fastp) {
+          // ---- S_t
+          mbar_wait2_sa(bar_s_sa + 8u * (uint32_t)buf, (s_par >> buf) & 1u, 10);
+          s_par ^= 1u << buf;
+          tcgen05_fence_after();
+          // One pass over the tile in two 32-key chunks: x = S + bias (+ mask), running row maximum and -- SPECULATIVELY, with
+          // the reference the row already has -- P = exp2(x - m_ref) packed to 16 bits.  The lazy rescale makes the speculation
+          // pay: the reference moves on ~7 % of the tiles only, so the exponentials do not have to wait for the maximum and
+          // the MUFU stream of one chunk overlaps the adds / maxima of the other (the two-phase version serialised
+          // LDS -> FADD -> LDTM -> FADD -> FMNMX -> MUFU per warp; the warps, not the MUFU pipe, bounded the kernel).  When a
+          // row does outgrow the reference the tile is simply recomputed from TMEM (S is still there: P overwrites it last).
+          float ps = 0.f;
+          auto pass = [&](const float mref, auto DO_EXP, auto MASKED) -> float {  // compile-time flags: straight-line code
+            constexpr bool do_exp = decltype(DO_EXP)::value, masked = decltype(MASKED)::value;
+            constexpr int KWS = KW > 0 ? KW : 32;
+            float mxa = -INFINITY, mxb = -INFINITY, psa = 0.f, psb = 0.f;
+            const uint64_t negm = pack2(-mref, -mref);
 #pragma unroll
-        for (int c = 0; c < KT / 2; ++c) {
-          const float p0 = A2_EX2(x[2 * c]), p1 = A2_EX2(x[2 * c + 1]);
-          if (!ones) ps0 += p0, ps1 += p1;
-          pk[c] = (fmt == FMT_BF16) ? pack_bf16(p0, p1) : pack_f16(p0, p1);
+            for (int c0 = 0; c0 < KT; c0 += 16) {  // 16 consecutive keys of one key row (registers: P 32 + S 16 + bias 16)
+              uint32_t v[16];
+#ifdef GRL_A2_DIAG_NOLDTM
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v[j] = 0;
+#else
+              tmem_ld16(ts + c0, v);  // in flight while the bias run is fetched
+#endif
+              const int kj = k0 + c0;  // first key of the run (CTA-uniform, multiple of 16)
+              const int kh = kj / KWS, kw0 = kj % KWS;
+              const int s0 = base_i - (kh * Wt + kw0) - 3;  // table index of key kj + 3
+              const int cpy = (-s0) & 3;
+              const float4* bp = reinterpret_cast<const float4*>(bias_h + (size_t)cpy * a.rows_pad + (s0 + cpy));
+              const uint32_t bps = bias_sa + (uint32_t)(cpy * a.rows_pad + (s0 + cpy)) * 4u;  // BS: LDS.128
+              float bsv[16];
+#pragma unroll
+              for (int qd = 0; qd < 4; ++qd) {
+                const float4 bb = A2_BIAS(BS ? lds128(bps - 16u * qd) : __ldg(bp - qd));
+                bsv[4 * qd + 0] = bb.w, bsv[4 * qd + 1] = bb.z, bsv[4 * qd + 2] = bb.y, bsv[4 * qd + 3] = bb.x;
+              }
+              if (masked) {
+                const int rid_lo = 3 * ((int)a1 + (int)(kh >= kh_th)) + (int)b1;
+                const float off_lo = (rid_lo != q_rid) ? kMaskLog2 : 0.f;
+                const float off_hi = (rid_lo + 1 != q_rid) ? kMaskLog2 : 0.f;
+#pragma unroll
+                for (int qd = 0; qd < 4; ++qd) {
+                  const float off = (kw0 + 4 * qd >= kw_th) ? off_hi : off_lo;
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) bsv[4 * qd + e] += off;
+                }
+              }
+#ifndef GRL_A2_DIAG_NOLDTM
+              tmem_ld_wait();
+#endif
+              uint64_t x2[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) x2[j] = add2(pack2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])), pack2(bsv[2 * j], bsv[2 * j + 1]));
+#pragma unroll
+              for (int j = 0; j < 8; j += 2) {
+                mxa = fmax3(mxa, lo2(x2[j]), hi2(x2[j]));
+                mxb = fmax3(mxb, lo2(x2[j + 1]), hi2(x2[j + 1]));
+              }
+              if (do_exp) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  const uint64_t y = add2(x2[j], negm);
+                  const float p0 = A2_EX2(lo2(y)), p1 = A2_EX2(hi2(y));
+                  if (!ones) psa += p0, psb += p1;
+                  pk[c0 / 2 + j] = (fmt == FMT_BF16) ? pack_bf16(p0, p1) : pack_f16(p0, p1);
+                }
+              }
+            }
+            ps = psa + psb;
+            return A2_MAX(fmaxf(mxa, mxb));
+          };
+          const bool first = (t == 0);
+          auto tile = [&](auto MASKED) {
+            using T = std::true_type;
+            using F = std::false_type;
+            // (no reference yet on the first tile of an item: maximum only)
+            const float mx = first ? pass(m_ref, F{}, MASKED) : pass(m_ref, T{}, MASKED);
+            if (__any_sync(0xffffffffu, first || mx - m_ref > kTau)) {
+              float delta = first ? mx : fmaxf(mx - m_ref, 0.f);
+              if (!(fabsf(delta) < 1e30f)) delta = 0.f;  // rows of a partial query tile hold garbage
+              m_ref += delta;
+              if (!first) {
+                // O_g must hold P V of every tile < t: peek at the next completion of the other buffer's barrier (see below)
+                mbar_wait2_sa(bar_s_sa + 8u * (uint32_t)(buf ^ 1), (s_par >> (buf ^ 1)) & 1u, 12);
+                tcgen05_fence_after();
+                const float sc = ex2(-delta);
+                uint32_t v[32];
+                tmem_ld32(to, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int e = 0; e < kDP; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) * sc);
+                tmem_st32(to, v);
+                l_run *= sc;
+              }
+              (void)pass(m_ref, T{}, MASKED);  // P against the new reference
+            }
+          };
+          if (need_mask) tile(std::true_type{});  // (item-uniform)
+          else tile(std::false_type{});
+          if (!ones) l_run += ps;
+        } else {
+          // ---- x = bias (+ mask) - m_ref first: these loads and adds do not depend on S and run while Q K^T is in flight.
+          // Nothing here may touch the per-stage metadata: a warpgroup that sat out the previous item is a whole item
+          // ahead of the producer, and an mbarrier parity wait only orders phases that are at most one apart.
+          float x[KT];
+          if (full_tile) {
+            constexpr int KWS = KW > 0 ? KW : 4;
+            constexpr int RW = (KWS >= 32) ? 32 : KWS;  // consecutive keys of one key row
+#pragma unroll
+            for (int r0 = 0; r0 < KT; r0 += RW) {
+              const int kj = k0 + r0;  // first key of the run (CTA-uniform, multiple of 4)
+              const int kh = kj / KWS, kw0 = kj % KWS;
+              const int s0 = base_i - (kh * Wt + kw0) - 3;  // table index of key kj + 3
+              const int cpy = (-s0) & 3;
+              const float4* bp = reinterpret_cast<const float4*>(bias_h + (size_t)cpy * a.rows_pad + (s0 + cpy));
+              const uint32_t bps = bias_sa + (uint32_t)(cpy * a.rows_pad + (s0 + cpy)) * 4u;  // BS: LDS.128
+              if (need_mask && mask_fast) {  // (item-uniform branch: windows without a mask skip the per-group selects)
+                const int rid_lo = 3 * ((int)a1 + (int)(kh >= kh_th)) + (int)b1;
+                const float off_lo = (rid_lo != q_rid) ? m_ref - kMaskLog2 : m_ref;
+                const float off_hi = (rid_lo + 1 != q_rid) ? m_ref - kMaskLog2 : m_ref;
+#pragma unroll
+                for (int qd = 0; qd < RW / 4; ++qd) {
+                  const float4 bb = A2_BIAS(BS ? lds128(bps - 16u * qd) : __ldg(bp - qd));
+                  const int j = r0 + 4 * qd;
+                  const float off = (kw0 + 4 * qd >= kw_th) ? off_hi : off_lo;
+                  x[j + 0] = bb.w - off, x[j + 1] = bb.z - off, x[j + 2] = bb.y - off, x[j + 3] = bb.x - off;
+                }
+              } else {
+#pragma unroll
+                for (int qd = 0; qd < RW / 4; ++qd) {
+                  const float4 bb = A2_BIAS(BS ? lds128(bps - 16u * qd) : __ldg(bp - qd));
+                  const int j = r0 + 4 * qd;
+                  x[j + 0] = bb.w - m_ref, x[j + 1] = bb.z - m_ref, x[j + 2] = bb.y - m_ref, x[j + 3] = bb.x - m_ref;
+                }
+              }
+            }
+          }
+          // ---- S_t
+          mbar_wait2_sa(bar_s_sa + 8u * (uint32_t)buf, (s_par >> buf) & 1u, 10);
+          s_par ^= 1u << buf;
+          tcgen05_fence_after();
+          const bool meta_mask = need_mask && !(full_tile && mask_fast);
+          if (!full_tile || meta_mask) mbar_wait_warp(&meta_full[st], rs.ph, 11);  // S_t ready => this fill is the current one
+          if (!full_tile) {
+#pragma unroll
+            for (int j = 0; j < KT; ++j) x[j] = (BS ? lds32f(bias_sa + 4u * (uint32_t)(base_i - lds32i(koff_sa + 4u * (st * KT + j))))
+                         : __ldg(bias_h + base_i - lds32i(koff_sa + 4u * (st * KT + j)))) - m_ref;
+          }
+#pragma unroll
+          for (int c0 = 0; c0 < KT; c0 += 32) {
+            A2_LDTM({
+              uint32_t v[32];
+              tmem_ld32(ts + c0, v);
+              tmem_ld_wait();
+              _Pragma("unroll") for (int j = 0; j < 32; ++j) x[c0 + j] += __uint_as_float(v[j]);
+            })
+          }
+          if (meta_mask) {
+#pragma unroll
+            for (int j = 0; j < KT; ++j)
+              if (lds32i(krid_sa + 4u * (st * KT + j)) != q_rid) x[j] += kMaskLog2;
+          }
+          if (k0 + KT > Nk) {  // after the add: K rows past Nk are stale shared memory, S there may be anything
+#pragma unroll
+            for (int j = 0; j < KT; ++j)
+              if (k0 + j >= Nk) x[j] = -INFINITY;
+          }
+          float mx0 = fmax3(x[0], x[1], x[2]), mx1 = fmax3(x[3], x[4], x[5]);
+#pragma unroll
+          for (int j = 6; j + 3 < KT; j += 4) {
+            mx0 = fmax3(mx0, x[j], x[j + 1]);
+            mx1 = fmax3(mx1, x[j + 2], x[j + 3]);
+          }
+          const float mx = A2_MAX(fmax3(mx0, mx1, fmaxf(x[KT - 2], x[KT - 1])));
+          // ---- lazy rescale: move the reference only when a row outgrew it by 2^kTau (always on the first tile)
+          const bool first = (t == 0);
+          if (__any_sync(0xffffffffu, first || mx > kTau)) {
+            float delta = first ? mx : fmaxf(mx, 0.f);
+            if (!(fabsf(delta) < 1e30f)) delta = 0.f;  // rows of a partial query tile hold garbage
+            m_ref += delta;
+#pragma unroll
+            for (int j = 0; j < KT; ++j) x[j] -= delta;
+            if (!first) {
+              // O_g must hold P V of every tile < t.  The NEXT completion of the other buffer's barrier (S(t+1) ready, or the
+              // closing completion when t is the last tile) is committed right after P V(t-1): peek at it (the wait at tile
+              // t+1 / in the epilogue consumes it), which keeps the wait exact and off the common path.
+              mbar_wait2_sa(bar_s_sa + 8u * (uint32_t)(buf ^ 1), (s_par >> (buf ^ 1)) & 1u, 12);
+              tcgen05_fence_after();
+              const float sc = ex2(-delta);
+              uint32_t v[32];
+              tmem_ld32(to, v);
+              tmem_ld_wait();
+#pragma unroll
+              for (int e = 0; e < kDP; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) * sc);
+              tmem_st32(to, v);
+              l_run *= sc;
+            }
+          }
+          // ---- P_t = exp2(x) -> 16-bit pairs -> TMEM (over S_t)
+          float ps0 = 0.f, ps1 = 0.f;
+#pragma unroll
+          for (int c = 0; c < KT / 2; ++c) {
+            const float p0 = A2_EX2(x[2 * c]), p1 = A2_EX2(x[2 * c + 1]);
+            if (!ones) ps0 += p0, ps1 += p1;
+            pk[c] = (fmt == FMT_BF16) ? pack_bf16(p0, p1) : pack_f16(p0, p1);
+          }
+          if (!ones) l_run += ps0 + ps1;
         }
-        if (!ones) l_run += ps0 + ps1;
         A2_STTM(tmem_st32(ts, pk));
         tmem_st_wait();
         tcgen05_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&p_full[2 * wg + buf]);
+        if (lane == 0) mbar_arrive_sa(p_full_sa + 8u * (uint32_t)buf);
       }
       // ---- epilogue: O_g final
       // closing completions: buffer ntiles & 1 (P V(ntiles-2) done), then buffer (ntiles+1) & 1 (P V(ntiles-1) done = O final)
-      mbar_wait_warp(&bar_s[2 * wg + (ntiles & 1)], s_cnt[ntiles & 1] & 1, 13);
-      ++s_cnt[ntiles & 1];
-      mbar_wait_warp(&bar_s[2 * wg + ((ntiles + 1) & 1)], s_cnt[(ntiles + 1) & 1] & 1, 14);
-      ++s_cnt[(ntiles + 1) & 1];
+      mbar_wait_warp(&bar_s[2 * wg + (ntiles & 1)], (s_par >> (ntiles & 1)) & 1u, 13);
+      s_par ^= 1u << (ntiles & 1);
+      mbar_wait_warp(&bar_s[2 * wg + ((ntiles + 1) & 1)], (s_par >> ((ntiles + 1) & 1)) & 1u, 14);
+      s_par ^= 1u << ((ntiles + 1) & 1);
       // "item consumed": the issuer may now commit the next item's S(0) / S(1) to these barriers (an mbarrier must not
       // complete twice before its waiter has looked: a parity wait cannot tell phases two apart)
       __syncwarp();
@@ -841,6 +1026,7 @@ int launch2_var(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap&
   }
   const int Nq = a.gq.wh * a.gq.ww;
   tg.n_qg = ceil_div(Nq, NWG * kQT);
+  tg.ntiles = ceil_div(a.gk.wh * a.gk.ww, kKT2);
   const long long per_head = (long long)a.B * (a.gq.H / a.gq.wh) * (a.gq.W / a.gq.ww) * tg.n_qg;
   GRL_REQUIRE(per_head * a.heads < (1ll << 31), "attn2: too many work items");
   tg.per_head = (int)per_head;

@@ -160,6 +160,18 @@ __device__ __forceinline__ void umma_ss(uint32_t tmem_d, uint64_t adesc, uint64_
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"((uint32_t)accumulate)
       : "memory");
 }
+// One lane of a converged warp (elect.sync).  Code under `if (elect_one())` is "one-lane uniform" to ptxas: operands of the
+// UTCHMMA / UTMALDG / UTCBAR instructions in it move to uniform registers with plain R2UR, where code under
+// `if (lane == 0)` gets an ELECT / R2UR.BROADCAST / BRA.U.ANY loop (about 13 instructions) around each of them.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 // All previously issued MMAs of this thread arrive on `bar` when they complete (implies fence::before_thread_sync).
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))

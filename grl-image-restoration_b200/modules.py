@@ -698,7 +698,15 @@ class GRL(nn.Module):
         if tuple(input_resolution) == tuple(self.input_resolution):
             t = {"table_w": self.table_w, "table_sh": self.table_sh, "table_sv": self.table_sv}
         else:
-            t = {k: v.to(device) for k, v in self._tables(input_resolution).items()}
+            # the coordinate tables depend only on the resolution: uploaded once per (resolution, device), which also
+            # keeps host->device copies out of a CUDA-graph capture
+            key = (tuple(input_resolution), str(device))
+            cache = self.__dict__.setdefault("_table_cache", {})
+            if key not in cache:
+                if len(cache) >= 16:
+                    cache.clear()
+                cache[key] = {k: v.to(device) for k, v in self._tables(input_resolution).items()}
+            t = dict(cache[key])
         for n in ("index_w", "index_sh_a2w", "index_sh_w2a", "index_sv_a2w", "index_sv_w2a", "mask_w", "mask_sh_a2w",
                   "mask_sh_w2a", "mask_sv_a2w", "mask_sv_w2a"):
             t[n] = _closed_form_marker()

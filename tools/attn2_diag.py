@@ -16,7 +16,10 @@ STUB = "-DGRL_A2_DIAG_NOBIAS -DGRL_A2_DIAG_NOEXP -DGRL_A2_DIAG_NOLDTM -DGRL_A2_D
 VARIANTS = {
     "base": "",
     "multi_issuer": "-DGRL_A2_MULTI_ISSUER",
-    "stub": STUB,
+    "multi_skew700": "-DGRL_A2_MULTI_ISSUER -DGRL_A2_SKEW=700",
+    "multi_skew1200": "-DGRL_A2_MULTI_ISSUER -DGRL_A2_SKEW=1200",
+    "multi_skew2400": "-DGRL_A2_MULTI_ISSUER -DGRL_A2_SKEW=2400",
+    "skew1200": "-DGRL_A2_SKEW=1200",
 }
 
 
