@@ -1112,7 +1112,10 @@ int launch_attn2(const AttnTcArgs& a, cudaStream_t st) {
   } else {
     if ((rc = make_token_map2(&tv, a.v, a.ldv, a.gk, a.B, tg.bw_k)) != GRL_OK) return rc;
   }
-  return launch2_nwg<3>(tq, tk, tv, a, tg, st);
+#ifndef GRL_A2_NWG  // A/B builds: 1 or 2 softmax warpgroups per CTA (how the time per tile depends on the co-resident warpgroups)
+#define GRL_A2_NWG 3
+#endif
+  return launch2_nwg<GRL_A2_NWG>(tq, tk, tv, a, tg, st);
 }
 
 }  // namespace tc

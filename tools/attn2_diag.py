@@ -15,11 +15,18 @@ AB = os.path.join(ROOT, "ab")
 STUB = "-DGRL_A2_DIAG_NOBIAS -DGRL_A2_DIAG_NOEXP -DGRL_A2_DIAG_NOLDTM -DGRL_A2_DIAG_NOSTTM -DGRL_A2_DIAG_NOMAX"
 VARIANTS = {
     "base": "",
+    # ingredients (results are garbage by construction)
+    "noexp": "-DGRL_A2_DIAG_NOEXP",
+    "nobias": "-DGRL_A2_DIAG_NOBIAS",
+    "noldtm_nosttm": "-DGRL_A2_DIAG_NOLDTM -DGRL_A2_DIAG_NOSTTM",
+    "stub": STUB,
+    "stub_nomma": STUB + " -DGRL_A2_DIAG_NOPV -DGRL_A2_DIAG_NOQK",
+    # structure (results stay correct)
+    "nwg1": "-DGRL_A2_NWG=1",
+    "nwg2": "-DGRL_A2_NWG=2",
     "multi_issuer": "-DGRL_A2_MULTI_ISSUER",
-    "multi_skew700": "-DGRL_A2_MULTI_ISSUER -DGRL_A2_SKEW=700",
+    "ilv": "-DGRL_A2_ILV",
     "multi_skew1200": "-DGRL_A2_MULTI_ISSUER -DGRL_A2_SKEW=1200",
-    "multi_skew2400": "-DGRL_A2_MULTI_ISSUER -DGRL_A2_SKEW=2400",
-    "skew1200": "-DGRL_A2_SKEW=1200",
 }
 
 
@@ -66,5 +73,8 @@ if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("cmd", choices=["build", "run"])
     ap.add_argument("--batch", type=int, default=16)
+    ap.add_argument("--only", default="", help="comma-separated subset of the variants")
     a = ap.parse_args()
+    if a.only:
+        VARIANTS = {k: v for k, v in VARIANTS.items() if k in a.only.split(",")}
     build() if a.cmd == "build" else run(a.batch)
