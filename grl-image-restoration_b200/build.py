@@ -19,8 +19,25 @@ def sources():
     return sorted(glob.glob(os.path.join(CSRC, "*.cu")))
 
 
+STAMP = os.path.join(PKG, "build", "defines.stamp")  # the GRL_NVCC_DEFINES the objects / library were compiled with
+
+
+def _defines():
+    return " ".join(os.environ.get("GRL_NVCC_DEFINES", "").split())
+
+
+def _stamp():
+    try:
+        with open(STAMP) as f:
+            return f.read().strip()
+    except OSError:
+        return ""  # no stamp: a production build (no defines)
+
+
 def _stale():
     if not os.path.exists(LIB):
+        return True
+    if _stamp() != _defines():  # an A/B build left behind (or asked for): never mistake it for the production library
         return True
     t = os.path.getmtime(LIB)
     deps = sources() + glob.glob(os.path.join(CSRC, "*.h")) + glob.glob(os.path.join(CSRC, "*.cuh"))
@@ -37,6 +54,8 @@ def build(force=False, verbose=False):
         raise RuntimeError("nvcc not found: cannot build libgrl_b200.so")
     objdir = os.path.join(PKG, "build")
     os.makedirs(objdir, exist_ok=True)
+    if _stamp() != _defines():
+        force = True  # different defines: every object is stale
     objs, procs = [], []
     for src in sources():
         obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
@@ -46,7 +65,7 @@ def build(force=False, verbose=False):
                             for h in glob.glob(os.path.join(CSRC, "*.h")) + glob.glob(os.path.join(CSRC, "*.cuh"))
                             + [os.path.join(os.path.dirname(PKG), "include", "grl_b200.h")])):
             continue
-        cmd = [nvcc] + NVCC_FLAGS + os.environ.get("GRL_NVCC_DEFINES", "").split() + ["-c", src, "-o", obj]  # A/B builds
+        cmd = [nvcc] + NVCC_FLAGS + _defines().split() + ["-c", src, "-o", obj]  # A/B builds
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     for src, p in procs:
         out, _ = p.communicate()
@@ -61,6 +80,8 @@ def build(force=False, verbose=False):
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}")
     os.replace(LIB + ".tmp", LIB)
+    with open(STAMP, "w") as f:
+        f.write(_defines())
     return LIB
 
 

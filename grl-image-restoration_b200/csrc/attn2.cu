@@ -703,9 +703,12 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
         const int k0 = t * KT, st = rs.st, buf = t & 1;
         const uint32_t ts = ts0 + buf * 64;
         const bool full_tile = (KW > 0) && (k0 + KT <= Nk);
-        // Tiles whose bias row is a closed-form run (full tile of a rectangular window, mask absent or closed-form) take the
-        // single-pass path below; ragged tiles / metadata masks keep the two-phase path after it.
-        const bool fastp = full_tile && (!need_mask || mask_fast);
+        // Tiles whose bias row is a closed-form run (full tile of a rectangular window, mask absent or closed-form) of a table
+        // that lives in SHARED memory take the single-pass path below; ragged tiles / metadata masks keep the two-phase path
+        // after it, and so do tables read through L1 (BS == false: the 64 x 128 stripes of the denoising models, 290 KB):
+        // the two-phase path has all 16 LDG.128 of a tile in flight before S is waited for, the chunked single pass would
+        // expose the L1 / L2 latency four times per tile (measured: cfg3 290 -> 322 ms per step).
+        const bool fastp = BS && full_tile && (!need_mask || mask_fast);
         uint32_t pk[32];
         if (fastp) {
           // ---- S_t

@@ -142,9 +142,7 @@ ATT = [  # B, H, W, (wh, ww), heads, shifted
 ]
 
 
-@pytest.mark.parametrize("fmt", [0, 1])
-@pytest.mark.parametrize("B,H,W,ws,heads,shifted", ATT)
-def test_attention_tc_window(tc, oracle, device, B, H, W, ws, heads, shifted, fmt):
+def _run_window(tc, oracle, device, B, H, W, ws, heads, shifted, fmt, table_fn=None):
     from grl_image_restoration_b200 import geometry as G
 
     d, nsl = 30, 3 * heads
@@ -155,6 +153,8 @@ def test_attention_tc_window(tc, oracle, device, B, H, W, ws, heads, shifted, fm
     qkv[:, :, : 2 * heads, :d] = F.normalize(qkv[:, :, : 2 * heads, :d], dim=-1)
     qkv[:, :, :heads] *= 9.0  # scaled queries (log2 domain logits up to ~9)
     table = torch.rand(heads, (2 * ws[0] - 1) * (2 * ws[1] - 1), generator=g) * 16 * tc.LOG2E
+    if table_fn is not None:
+        table = table_fn(table)
     s = ws[0] // 2 if shifted else 0
     # reference through the oracle's partition / roll helpers
     t = qkv.view(B, H, W, nsl * 32)
@@ -176,6 +176,29 @@ def test_attention_tc_window(tc, oracle, device, B, H, W, ws, heads, shifted, fm
     err = (got - ref).abs().max().item()
     assert err <= 4e-2 * max(1.0, ref.abs().max().item()), err
     assert (got - ref).abs().mean().item() <= 6e-3
+
+
+@pytest.mark.parametrize("fmt", [0, 1])
+@pytest.mark.parametrize("B,H,W,ws,heads,shifted", ATT)
+def test_attention_tc_window(tc, oracle, device, B, H, W, ws, heads, shifted, fmt):
+    _run_window(tc, oracle, device, B, H, W, ws, heads, shifted, fmt)
+
+
+@pytest.mark.parametrize("slope", [0.6, 6.0])
+@pytest.mark.parametrize("shifted", [False, True])
+def test_attention_tc_lazy_rescale_path(tc, oracle, device, slope, shifted):
+    """A bias that GROWS with the key row (by `slope` log2 units per row, 2 rows per 64-key tile) makes every row's running
+    maximum outgrow its reference by more than 2^8 repeatedly (slope 6: on every tile; 0.6: every ~7 tiles), i.e. the
+    kernel's speculative exponentials are discarded, O is rescaled in TMEM and the tile recomputed -- the path the random
+    tables of the other tests almost never take after the first tile."""
+    ws = (32, 32)
+
+    def grow(table):
+        rows = torch.arange(table.shape[1])
+        dh = rows // (2 * ws[1] - 1) - (ws[0] - 1)  # query row - key row of this relative position
+        return table * 0.25 + (-slope * dh.float()).unsqueeze(0)
+
+    _run_window(tc, oracle, device, 2, 32, 64, ws, 3, shifted, 0, table_fn=grow)
 
 
 @pytest.mark.parametrize("B,H,W,stripe,df,heads,shifted", [(1, 16, 32, (8, 16), 2, 2, True), (1, 64, 64, (64, 64), 2, 3, True),

@@ -1,4 +1,6 @@
 """Host-side logic that needs no GPU: tensor-core eligibility, checkpoint ingestion, constructor guards."""
+import os
+
 import pytest
 import torch
 
@@ -77,3 +79,21 @@ def test_checkpoint_ingestion_variants(pkg, tmp_path):
     m = fresh()
     checkpoint.load_reference_checkpoint(m, {k: v.clone() for k, v in sd.items()})
     assert same(m)
+
+
+def test_build_stamp_tracks_nvcc_defines(pkg, monkeypatch):
+    """An A/B build (GRL_NVCC_DEFINES) must never be mistaken for the production library: the build records the defines it
+    was compiled with and a mismatch makes the library stale."""
+    from grl_image_restoration_b200 import build as b
+
+    if not os.path.exists(b.LIB):
+        pytest.skip("library not built")
+    monkeypatch.delenv("GRL_NVCC_DEFINES", raising=False)
+    monkeypatch.setattr(b, "_stamp", lambda: "")
+    assert not b._stale()
+    monkeypatch.setenv("GRL_NVCC_DEFINES", "-DGRL_A2_DIAG_NOEXP")
+    assert b._stale()  # production stamp, A/B build requested
+    monkeypatch.setattr(b, "_stamp", lambda: "-DGRL_A2_DIAG_NOEXP")
+    assert not b._stale()
+    monkeypatch.delenv("GRL_NVCC_DEFINES")
+    assert b._stale()  # A/B library left behind, production requested
