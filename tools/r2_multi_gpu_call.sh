@@ -21,7 +21,7 @@ if [ "$N" -le 2 ]; then  # single-GPU checks that ride along on the small box
   head -c 300 gpurun_out/r2_bench_cfg3.json | tee -a "$LOG"; echo | tee -a "$LOG"
 fi
 run cfg5 --workload cfg5 --steps 5 --warmup 3
-run cfg4_weak --workload cfg4 --steps 5 --warmup 3
 if [ "$N" -le 2 ]; then
+  run cfg4_weak --workload cfg4 --steps 5 --warmup 3
   run cfg4_strong --workload cfg4 --scaling strong --steps 5 --warmup 3
 fi
