@@ -10,12 +10,14 @@
 //   * O accumulates in TMEM across key tiles (tcgen05.mma accumulate); the running-max rescale is LAZY: O is touched
 //     by the softmax warps only when a row's maximum grew by more than 2^8 since its reference was fixed, which is
 //     rare after the first tile -- the 32-register output accumulator and its per-tile fold are gone;
-//   * while one warpgroup waits for its P V / next Q K^T round trip, the other NWG-1 keep the MUFU pipe busy -- the
-//     exp2 unit (16 / clk / SM) is the binding resource at head_dim 32, not the tensor pipe.
+//   * the softmax is ONE pass per tile with speculative exponentials (the lazy rescale makes the reference known before the
+//     row maximum of the tile is): tcgen05.ld / bias LDS / packed FADD2 / FMNMX3 / MUFU.EX2 / pack as straight-line code;
+//   * measured: at head_dim 32 neither the tensor pipe (11 % active) nor the exp2 unit (47 %) binds, the
+//     SM's LSU / TMEM data path does -- 80 KB per 128 x 64 score tile for S out of TMEM, P back and the bias from shared memory.
 //
-// Roles (threads = NWG * 128 + 32 + NWG * 32): warpgroups 0..NWG-1 softmax; warp 4 NWG = TMA producer; warps 4 NWG + 1 + g =
-// single-thread tcgen05.mma issuer of warpgroup g.  (No setmaxnreg: the register pool of a CTA is what its own warps release, and 576 threads at 112
-// registers already use the whole file.)
+// Roles (threads = NWG * 128 + 64): warpgroups 0..NWG-1 softmax; warp 4 NWG = TMA producer; warp 4 NWG + 1 = the MMA issuer (one
+// elected thread issues every tcgen05.mma; GRL_A2_MULTI_ISSUER builds one issuer warp per warpgroup instead: no faster).
+// (No setmaxnreg: the register pool of a CTA is what its own warps release.)
 //
 // TMEM columns per warpgroup g (base 160 g): [0, 64) = S buffer 0, [64, 128) = S buffer 1, [128, 160) = O_g.  S_g(t) lands
 // in buffer t & 1 and is overwritten in place by P_g(t) (16-bit pairs in the first 32 columns of the buffer).  Q K^T runs
