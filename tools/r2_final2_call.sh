@@ -1,3 +1,5 @@
+# The last measurement call of round 2 (persistent GEMM kernels on by default).  NOT run in full: the round's GPU budget ended
+# after its operator-test leg (profiles/r2_persistent_gemm_optests.log); kept as the command list for whoever re-takes the numbers.
 set -u
 mkdir -p gpurun_out
 LOG=gpurun_out/r2_final2.log; : > "$LOG"
