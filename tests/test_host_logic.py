@@ -97,3 +97,35 @@ def test_build_stamp_tracks_nvcc_defines(pkg, monkeypatch):
     assert not b._stale()
     monkeypatch.delenv("GRL_NVCC_DEFINES")
     assert b._stale()  # A/B library left behind, production requested
+
+
+def _run_bench(args, env_extra=None):
+    import json
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, **(env_extra or {}))
+    p = subprocess.run([sys.executable, os.path.join(root, "bench.py")] + args, stdout=subprocess.PIPE, stderr=subprocess.PIPE,
+                       text=True, env=env, timeout=600, cwd=root)
+    assert p.returncode == 0, p.stderr[-2000:]
+    lines = [l for l in p.stdout.split("\n") if l.strip()]
+    return [json.loads(l) for l in lines]
+
+
+def test_bench_reference_arm_contract():
+    """bench.py --impl reference: ONE JSON line on stdout (CPU only, the reference's own forward), same metric / unit / config
+    keys as our arm, a cpu_baseline that says what was sampled, an e2e block with zero copies; ranks > 0 print nothing."""
+    out = _run_bench(["--impl", "reference", "--workload", "cfg1", "--steps", "1", "--warmup", "0"])
+    assert len(out) == 1
+    d = out[0]
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["unit"] == "Mpix/s" and d["higher_is_better"] is True and d["vs_baseline"] is None
+    assert d["value"] > 0 and d["cpu_baseline"]["value"] == d["value"] and d["cpu_baseline"]["cores"] >= 1
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and "64x64" in d["cpu_baseline"]["sample"]
+    assert "64x64" in d["config"]["workload"]  # the line names the bounded sample it measured
+    assert d["e2e"] == {"value": d["value"], "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert _run_bench(["--impl", "reference", "--gpus", "2", "--workload", "cfg1", "--steps", "1", "--warmup", "0"],
+                      {"RANK": "1", "LOCAL_RANK": "1", "WORLD_SIZE": "2"}) == []
