@@ -129,3 +129,41 @@ def test_bench_reference_arm_contract():
     assert d["e2e"] == {"value": d["value"], "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert _run_bench(["--impl", "reference", "--gpus", "2", "--workload", "cfg1", "--steps", "1", "--warmup", "0"],
                       {"RANK": "1", "LOCAL_RANK": "1", "WORLD_SIZE": "2"}) == []
+
+
+@pytest.mark.parametrize("kw,size", [(dict(), 32), (dict(embed_dim=60, heads=3, window=8, stripe=(8, 16), df=2), 48),
+                                     (dict(window=4, stripe=(16, 8), df=4, depth=2), 32)])
+def test_attention_counts_match_the_materialised_attention(pkg, oracle, monkeypatch, kw, size):
+    """flops.attention_counts (the numerator of bench.py's roofline) == the number of score elements the oracle actually
+    puts through softmax in one forward (it materialises every (N1 x N2) attention map), and f_attn = 4 head_dim per element."""
+    from grl_image_restoration_b200 import flops
+
+    cfg = pkg.configs.micro_config(img_size=size, **kw)
+    sd = oracle.synth_state_dict(cfg, seed=0, style="init")
+    seen = []
+    real = torch.softmax
+
+    def counting(t, dim=-1, **k):
+        seen.append(tuple(t.shape))
+        return real(t, dim=dim, **k)
+
+    monkeypatch.setattr(torch, "softmax", counting)
+    with torch.no_grad():
+        oracle.grl_forward(sd, cfg, oracle.synth_input((1, 3, size, size), seed=1))
+    monkeypatch.undo()
+    total = sum(int(torch.tensor(s).prod()) for s in seen)
+    counts = flops.attention_counts(cfg, (size, size))
+    assert counts["score_elems"] == total
+    d = cfg["embed_dim"] // 2 // cfg["num_heads_window"][0]
+    assert counts["f_attn"] == 4 * d * total and counts["f_qk"] * 2 == counts["f_attn"]
+
+
+def test_attention_counts_of_the_baseline_configs(pkg):
+    """The per-image figures DESIGN.md section 5 and the bench line quote (GFLOP of QK^T + PV, G score elements)."""
+    from grl_image_restoration_b200 import flops
+
+    want = {"cfg4": (("base", "sr", 4, 256), 2899.1029248, 24.15919104), "cfg2": (("small", "sr", 4, 256), 412.316860416, 3.221225472),
+            "cfg3": (("base", "dn", 1, 256), 4831.838208, 40.2653184), "cfg5": (("base", "deblur", 1, 480), 2388.7872, 19.90656)}
+    for name, ((v, t, s, sz), gf, ge) in want.items():
+        c = flops.attention_counts(pkg.configs.grl_config(v, t, s, sz), (sz, sz))
+        assert abs(c["f_attn"] / 1e9 - gf) < 1e-6 and abs(c["score_elems"] / 1e9 - ge) < 1e-6, name
