@@ -7,8 +7,11 @@
  * adds.  Conventions for every function:
  *   - plain pointers + sizes only; all data pointers are DEVICE pointers unless the name ends in
  *     _host; `stream` is a cudaStream_t passed as void*;
- *   - no allocation, no synchronisation, no global mutable state besides the per-thread error
- *     string; re-entrant per stream;
+ *   - no allocation, no synchronisation; re-entrant per stream.  Process-wide state is limited to: the
+ *     per-thread error string, an atomic launch counter (grl_launch_count), the attention-kernel
+ *     selector (grl_tc_attn_variant) and the environment switches read once (GRL_ATTN_SPLIT,
+ *     GRL_GEMM_PERSISTENT, GRL_ATTN2_*), the per-device "shared-memory attribute set" flags, and the
+ *     watchdog record of grl_tc_attn2_debug.  None of it depends on the data of a call;
  *   - returns 0 on success, a negative GrlStatus otherwise; grl_last_error() gives the message
  *     (the Python wrappers raise RuntimeError -- same behaviour as a failing ATen call).
  * Activations are channels-last: a (B, L, C) token tensor is the same memory as (B, H, W, C).
